@@ -1,0 +1,81 @@
+"""Synthetic condensed linear-MPC instances for configs C4/C5 (bench and test INPUT synthesis only).
+
+The reference ships exactly one instance (example/, pHorizon=1) and no MPC generator; SURVEY 7 "Hard parts"
+asks the bench to synthesise the condensed matrices and document how.  This is that recipe, in the
+reference's own conventions (PQP_CPU.c:5-6, 373-382, 940-941):
+
+    x_{k+1} = A x_k + B u_k + E d_k,   y_k = C x_k           (nState, nInput, nOutput = nInput, nDis = 1)
+    stacked over the horizon:  Xs = Phi x + Gam U + Gd D
+    cost   1/2 U'Qp U + Fp(x)'U + 1/2 Mp,   Qp = Gam'Qb Gam + Rb,  Fp(x) = Fp1 D + Fp2 x - Fp3
+           Fp2 = Gam'Qb Phi,  Fp1 = Gam'Qb Gd,  Fp3 = Gam'Qb r (tracking offset)
+    constraints  Gp U <= Kp,  Gp = [I; -I; C Gam; -C Gam]   (N = 4*pHorizon*nInput rows, M = pHorizon*nInput)
+
+Bounds umax = 20 (the example's Kp, example/Kp.txt), ymax = 30 and states x ~ N(0, 60^2) put the instance in the
+regime of the shipped example: the dual starts at 1000 (PQP_CPU.c:710), theta sits at its floor 5, and 1000
+updates bring the KKT residual to ~1e-3 with a few percent of the 480 constraints active (11-60 depending on x).
+
+Everything is built in float64 with a seeded numpy Generator and rounded once to float32.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def condensed_mpc(seed: int, pH: int = 30, nS: int = 12, nI: int = 4, n_states: int = 4096, x_scale: float = 60.0,
+                  umax: float = 20.0, ymax: float = 30.0):
+    """Returns (problem dict for pqp.Solver, pqp Dims, X [n_states x nS] float32)."""
+    import pqp_for_mpc_b200 as pqp
+
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((nS, nS))
+    A *= 0.95 / np.abs(np.linalg.eigvals(A)).max()  # stable, spectral radius 0.95
+    Bm = rng.standard_normal((nS, nI))
+    Cm = rng.standard_normal((nI, nS)) / np.sqrt(nS)
+    E = rng.standard_normal((nS, 1)) * 0.1
+    Qb1 = np.eye(nS) + 0.1 * (lambda W: W @ W.T)(rng.standard_normal((nS, nS))) / nS
+    Rb1 = 0.1 * np.eye(nI)
+
+    M, N = pH * nI, 4 * pH * nI
+    Phi = np.zeros((pH * nS, nS))
+    Gam = np.zeros((pH * nS, M))
+    Gd = np.zeros((pH * nS, pH))
+    Ak = np.eye(nS)
+    pows = [np.eye(nS)]
+    for k in range(pH):
+        pows.append(pows[-1] @ A)
+    for k in range(pH):
+        Phi[k * nS:(k + 1) * nS] = pows[k + 1]
+        for j in range(k + 1):
+            Gam[k * nS:(k + 1) * nS, j * nI:(j + 1) * nI] = pows[k - j] @ Bm
+            Gd[k * nS:(k + 1) * nS, j:j + 1] = pows[k - j] @ E
+    Qb = np.kron(np.eye(pH), Qb1)
+    Rb = np.kron(np.eye(pH), Rb1)
+    Cs = np.kron(np.eye(pH), Cm)
+
+    Qp = Gam.T @ Qb @ Gam + Rb
+    Qp = 0.5 * (Qp + Qp.T)
+    Qp_inv = np.linalg.inv(Qp)
+    r = rng.standard_normal(pH * nS) * 0.5
+    Fp2 = Gam.T @ Qb @ Phi
+    Fp1 = Gam.T @ Qb @ Gd
+    Fp3 = Gam.T @ Qb @ r
+    D = rng.standard_normal(pH) * 0.1
+    CG = Cs @ Gam
+    Gp = np.vstack([np.eye(M), -np.eye(M), CG, -CG])
+    Kp = np.concatenate([np.full(2 * M, umax), np.full(2 * M, ymax)])
+
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    prob = dict(Qp_inv=f32(Qp_inv), Gp=f32(Gp), Kp=f32(Kp), Fp1=f32(Fp1), Fp2=f32(Fp2), Fp3=f32(Fp3), D=f32(D),
+                Mp1=f32(Phi.T @ Qb @ Phi), Mp2=f32(Gd.T @ Qb @ Phi), Mp3=f32(Gd.T @ Qb @ Gd),
+                Mp4=f32(-2 * Phi.T @ Qb @ r), Mp5=f32(-2 * Gd.T @ Qb @ r), Mp6=f32([r @ Qb @ r]))
+    d = pqp.dims_mpc(pH, nS, nI, nI, 1)
+    X = f32(rng.standard_normal((n_states, nS)) * x_scale)
+    prob["x"] = X[0].copy()
+    return prob, d, X
+
+
+def shard_range(total: int, world: int, rank: int):
+    """Contiguous shard [lo, hi) of `total` independent problems for `rank` of `world`."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -1,0 +1,669 @@
+/*
+ * pqp_api.cu -- host side of the C ABI in include/pqp.h: handle, setup, solve, recovery.
+ *
+ * Mirrors the call sequence of PQP_CPU.c's main() (:988-999):
+ *   input -> Gauss_Jordan -> computeFp -> computeMp -> convertToDual -> solveQuadraticDual -> computeUfromY
+ * split into the x-independent part (pqp_setup: GQ, Qd, theta) and the per-state part
+ * (pqp_solve_batch: Fp(x), Fd(x), the loop; pqp_recover_primal: U).  Gauss_Jordan is not needed:
+ * Qp only feeds Jp inside terminate(), which SURVEY 3.3 replaces by reductions on g = Qd y + Fd.
+ *
+ * There is no CPU fallback anywhere in this file: without an sm_100 device every entry point
+ * that computes returns PQP_ERR_NO_DEVICE.
+ */
+#include "pqp_internal.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static thread_local char g_cuda_err[512] = "";
+
+#define CK(call)                                                                                          \
+	do {                                                                                              \
+		cudaError_t e__ = (call);                                                                 \
+		if (e__ != cudaSuccess) {                                                                 \
+			snprintf(g_cuda_err, sizeof g_cuda_err, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, \
+				 cudaGetErrorString(e__));                                                \
+			return e__ == cudaErrorMemoryAllocation ? PQP_ERR_ALLOC : PQP_ERR_CUDA;           \
+		}                                                                                         \
+	} while (0)
+
+struct pqp_handle {
+	pqp_dims d;
+	pqp_opts o;
+	int device, num_sms;
+	size_t smem_optin;
+	cudaStream_t stream;
+	cudaEvent_t ev0, ev1;
+	int ev_valid;
+	int ldq;
+	int have_primal, have_fp_model;
+	/* x-independent device data */
+	float *Q, *QT, *theta, *GQ, *Gp, *Qp_inv, *Kp, *Fp1, *Fp2, *Fp3, *Fp_const, *D;
+	float *Mp1, *Mp2, *Mp3, *Mp4, *Mp5, *Mp6;
+	float Mp0;
+	float *QpT, *QnT; /* batched operands, built on first batched solve */
+	int Kpad, Ipad;
+	/* per-batch workspace */
+	int cap;
+	float *X, *Db, *Fp, *Fd, *Md, *Y, *U, *Tmp;
+	pqp_status *st;
+	int fp_B; /* problems whose Fp is cached from the last solve */
+	/* single-problem loop state */
+	float *ybuf0, *ybuf1, *partials;
+	unsigned *barrier;
+	int *result_buf;
+	int gemv_grid, gemv_resident;
+	int l2_window_set;
+	long long launches;
+	const char *last_kernel;
+};
+
+const char *pqp_last_cuda_error(void) { return g_cuda_err; }
+
+void pqp_default_opts(pqp_opts *o)
+{
+	memset(o, 0, sizeof *o);
+	o->theta_floor = 5.0f;  /* PQP_CPU.c:240 */
+	o->y_init = 1000.0f;    /* PQP_CPU.c:710 */
+	o->erc = o->eac = o->eaj = o->erj = 1e-6f; /* PQP_CPU.c:19-22 */
+	o->order = PQP_ORDER_FAST;
+	o->device = -1;
+	o->max_iters = 100000;
+	o->check_every = 8;
+	o->batch_capacity = 1;
+	o->use_tensor_cores = 1;
+	o->l2_persist = 1;
+}
+
+int pqp_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	int ok = 0;
+	for (int i = 0; i < n; i++) {
+		int major = 0;
+		if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+	}
+	return ok;
+}
+
+template <typename T> static int dalloc(T **p, size_t n)
+{
+	*p = NULL;
+	if (n == 0) n = 1;
+	cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+	if (e != cudaSuccess) {
+		snprintf(g_cuda_err, sizeof g_cuda_err, "cudaMalloc(%zu bytes) -> %s", n * sizeof(T), cudaGetErrorString(e));
+		cudaGetLastError();
+		return PQP_ERR_ALLOC;
+	}
+	return PQP_OK;
+}
+
+/* allocate + copy from a host-or-device source (UVA sorts out the direction) */
+static int upload(pqp_handle *h, float **dst, const float *src, size_t n)
+{
+	*dst = NULL;
+	if (!src || n == 0) return PQP_OK;
+	int rc = dalloc(dst, n);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyDefault, h->stream));
+	return PQP_OK;
+}
+
+static int open_device(pqp_handle *h, const pqp_opts *opts)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		return PQP_ERR_NO_DEVICE;
+	}
+	int dev = opts->device;
+	if (dev < 0) CK(cudaGetDevice(&dev));
+	if (dev >= n) return PQP_ERR_INVALID;
+	int major = 0;
+	CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+	if (major != 10) return PQP_ERR_NO_DEVICE; /* the kernels are sm_100a-only */
+	CK(cudaSetDevice(dev));
+	h->device = dev;
+	CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev));
+	int optin = 0;
+	CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+	h->smem_optin = (size_t)optin;
+	CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&h->ev0));
+	CK(cudaEventCreate(&h->ev1));
+	return PQP_OK;
+}
+
+static int ensure_capacity(pqp_handle *h, int B)
+{
+	if (B <= h->cap) return PQP_OK;
+	const int M = h->d.M, N = h->d.N;
+	float **bufs[] = { &h->X, &h->Db, &h->Fp, &h->Fd, &h->Md, &h->Y, &h->U, &h->Tmp };
+	for (size_t i = 0; i < sizeof bufs / sizeof bufs[0]; i++) {
+		if (*bufs[i]) cudaFree(*bufs[i]);
+		*bufs[i] = NULL;
+	}
+	if (h->st) cudaFree(h->st);
+	h->st = NULL;
+	h->cap = 0;
+	h->fp_B = 0;
+	int rc = 0;
+	rc |= dalloc(&h->X, (size_t)B * (h->d.nState > 0 ? h->d.nState : 1));
+	rc |= dalloc(&h->Db, (size_t)B * (h->d.nDisH > 0 ? h->d.nDisH : 1));
+	rc |= dalloc(&h->Fp, (size_t)B * (M > 0 ? M : 1));
+	rc |= dalloc(&h->Fd, (size_t)B * N);
+	rc |= dalloc(&h->Md, (size_t)B);
+	rc |= dalloc(&h->Y, (size_t)B * N);
+	rc |= dalloc(&h->U, (size_t)B * (M > 0 ? M : 1));
+	rc |= dalloc(&h->Tmp, (size_t)B * (M > 0 ? M : 1));
+	rc |= dalloc(&h->st, (size_t)B);
+	if (rc) return PQP_ERR_ALLOC;
+	h->cap = B;
+	return PQP_OK;
+}
+
+/* theta, transposes, loop state: everything that only needs Q on the device */
+static int finish_setup(pqp_handle *h)
+{
+	const int N = h->d.N, ldq = h->ldq;
+	const int strict = h->o.order == PQP_ORDER_STRICT;
+	int rc;
+	if ((rc = dalloc(&h->theta, N))) return rc;
+	if (strict) {
+		if ((rc = dalloc(&h->QT, (size_t)N * ldq))) return rc;
+		CK(cudaMemsetAsync(h->QT, 0, (size_t)N * ldq * sizeof(float), h->stream));
+		CK(pqp_launch_transpose(h->QT, ldq, h->Q, ldq, N, N, h->stream));
+		CK(pqp_launch_theta(h->theta, h->QT, ldq, N, h->o.theta_floor, 1, h->stream));
+		h->launches += 2;
+	} else {
+		CK(pqp_launch_theta(h->theta, h->Q, ldq, N, h->o.theta_floor, 0, h->stream));
+		h->launches += 1;
+	}
+	if ((rc = dalloc(&h->ybuf0, ldq)) || (rc = dalloc(&h->ybuf1, ldq))) return rc;
+	if ((rc = dalloc(&h->barrier, 4)) || (rc = dalloc(&h->result_buf, 4))) return rc;
+
+	/* persistent-kernel geometry: one CTA per SM, but never fewer than 4 rows per CTA */
+	int grid = h->num_sms;
+	if (grid > (N + 3) / 4) grid = (N + 3) / 4;
+	if (grid < 1) grid = 1;
+	h->gemv_grid = grid;
+	if ((rc = dalloc(&h->partials, (size_t)2 * grid * 8))) return rc;
+	/* rows of each slab that fit in shared memory next to y and the partial sums */
+	size_t base;
+	pqp_gemv_smem_bytes(N, ldq, grid, 0, &base);
+	const size_t budget = h->smem_optin > 1024 ? h->smem_optin - 1024 : 0;
+	int res = 0;
+	if (base < budget) res = (int)((budget - base) / ((size_t)ldq * sizeof(float)));
+	const int rows_max = (N + grid - 1) / grid + 1;
+	if (res > rows_max) res = rows_max;
+	if (base > budget) {
+		h->gemv_grid = 0; /* y does not fit in shared memory: persistent kernel unavailable */
+		res = 0;
+	}
+	const char *env = getenv("PQP_GEMV_RESIDENT");
+	if (env) {
+		int v = atoi(env);
+		if (v >= 0 && v < res) res = v;
+	}
+	h->gemv_resident = res;
+
+	if ((rc = ensure_capacity(h, h->o.batch_capacity > 0 ? h->o.batch_capacity : 1))) return rc;
+	CK(cudaStreamSynchronize(h->stream));
+	return PQP_OK;
+}
+
+static int l2_persist_window(pqp_handle *h, int enable)
+{
+	if (!h->o.l2_persist) return PQP_OK;
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, h->device));
+	if (prop.persistingL2CacheMaxSize <= 0 || prop.accessPolicyMaxWindowSize <= 0) return PQP_OK;
+	cudaStreamAttrValue v;
+	memset(&v, 0, sizeof v);
+	if (enable) {
+		const size_t qbytes = (size_t)h->d.N * h->ldq * sizeof(float);
+		size_t persist = (size_t)prop.persistingL2CacheMaxSize;
+		const char *env = getenv("PQP_L2_PERSIST_MB");
+		if (env) persist = (size_t)atoi(env) << 20;
+		if (persist == 0) return PQP_OK;
+		if (persist > (size_t)prop.persistingL2CacheMaxSize) persist = (size_t)prop.persistingL2CacheMaxSize;
+		CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+		size_t win = qbytes < (size_t)prop.accessPolicyMaxWindowSize ? qbytes : (size_t)prop.accessPolicyMaxWindowSize;
+		v.accessPolicyWindow.base_ptr = (void *)h->Q;
+		v.accessPolicyWindow.num_bytes = win;
+		float ratio = (float)((double)persist / (double)win);
+		v.accessPolicyWindow.hitRatio = ratio > 1.0f ? 1.0f : ratio;
+		v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	} else {
+		v.accessPolicyWindow.num_bytes = 0;
+	}
+	CK(cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v));
+	h->l2_window_set = enable;
+	return PQP_OK;
+}
+
+int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p, const pqp_opts *opts_in)
+{
+	if (!out || !dims || !p) return PQP_ERR_INVALID;
+	*out = NULL;
+	if (dims->M <= 0 || dims->N <= 0 || dims->nState < 0 || dims->nDisH < 0) return PQP_ERR_INVALID;
+	if (!p->Qp_inv || !p->Gp || !p->Kp) return PQP_ERR_INVALID;
+	if (dims->nState > 0 && (!p->Fp2 || !p->Fp3)) return PQP_ERR_INVALID;
+	if (dims->nState > 0 && dims->nDisH > 0 && (!p->Fp1 || !p->D)) return PQP_ERR_INVALID;
+	if (dims->nState == 0 && !p->Fp) return PQP_ERR_INVALID;
+	pqp_opts o;
+	if (opts_in) o = *opts_in; else pqp_default_opts(&o);
+	if (o.order != PQP_ORDER_FAST && o.order != PQP_ORDER_STRICT) return PQP_ERR_INVALID;
+	if (o.check_every < 1) o.check_every = 1;
+
+	pqp_handle *h = (pqp_handle *)calloc(1, sizeof *h);
+	if (!h) return PQP_ERR_ALLOC;
+	h->d = *dims;
+	h->o = o;
+	h->last_kernel = "none";
+	int rc = open_device(h, &o);
+	if (rc) { pqp_destroy(h); return rc; }
+
+	const int M = dims->M, N = dims->N, nS = dims->nState, nd = dims->nDisH;
+	h->ldq = pqp_round_up(N, 32);
+	h->have_primal = 1;
+	h->have_fp_model = 1;
+	h->Mp0 = p->Mp0;
+#define UP(field, n)                                                  \
+	if ((rc = upload(h, &h->field, p->field, (size_t)(n)))) {     \
+		pqp_destroy(h);                                       \
+		return rc;                                            \
+	}
+	UP(Qp_inv, (size_t)M * M) UP(Gp, (size_t)N * M) UP(Kp, N)
+	UP(Fp1, (size_t)M * nd) UP(Fp2, (size_t)M * nS) UP(Fp3, M) UP(D, nd)
+	if (p->Mp1 && p->Mp2 && p->Mp3 && p->Mp4 && p->Mp5 && p->Mp6 && nS > 0) {
+		UP(Mp1, (size_t)nS * nS) UP(Mp2, (size_t)nd * nS) UP(Mp3, (size_t)nd * nd) UP(Mp4, nS) UP(Mp5, nd) UP(Mp6, 1)
+	}
+#undef UP
+	if (nS == 0 && (rc = upload(h, &h->Fp_const, p->Fp, M))) { pqp_destroy(h); return rc; }
+
+	const int strict = o.order == PQP_ORDER_STRICT;
+	if ((rc = dalloc(&h->GQ, (size_t)N * M)) || (rc = dalloc(&h->Q, (size_t)N * h->ldq))) { pqp_destroy(h); return rc; }
+	cudaError_t e = cudaMemsetAsync(h->Q, 0, (size_t)N * h->ldq * sizeof(float), h->stream);
+	/* GQ = Gp*Qp_inv (PQP_CPU.c:492), Qd = GQ*Gp' (PQP_CPU.c:442) */
+	if (e == cudaSuccess) {
+		if (strict) {
+			e = pqp_launch_matmul_strict(h->GQ, M, h->Gp, M, h->Qp_inv, M, 0, N, M, M, h->stream);
+			if (e == cudaSuccess) e = pqp_launch_matmul_strict(h->Q, h->ldq, h->GQ, M, h->Gp, M, 1, N, M, N, h->stream);
+		} else {
+			e = pqp_launch_matmul_simt(h->GQ, M, h->Gp, M, h->Qp_inv, M, 0, N, M, M, h->stream);
+			if (e == cudaSuccess) e = pqp_launch_matmul_simt(h->Q, h->ldq, h->GQ, M, h->Gp, M, 1, N, M, N, h->stream);
+		}
+		h->launches += 2;
+	}
+	if (e != cudaSuccess) {
+		snprintf(g_cuda_err, sizeof g_cuda_err, "setup GEMMs -> %s", cudaGetErrorString(e));
+		pqp_destroy(h);
+		return PQP_ERR_CUDA;
+	}
+	if ((rc = finish_setup(h))) { pqp_destroy(h); return rc; }
+	*out = h;
+	return PQP_OK;
+}
+
+int pqp_setup_dual(pqp_handle **out, int N, const float *Qd, int M, const float *Gp, const float *Qp_inv,
+		   const pqp_opts *opts_in)
+{
+	if (!out || N <= 0 || !Qd) return PQP_ERR_INVALID;
+	*out = NULL;
+	pqp_opts o;
+	if (opts_in) o = *opts_in; else pqp_default_opts(&o);
+	if (o.order != PQP_ORDER_FAST && o.order != PQP_ORDER_STRICT) return PQP_ERR_INVALID;
+	if (o.check_every < 1) o.check_every = 1;
+	pqp_handle *h = (pqp_handle *)calloc(1, sizeof *h);
+	if (!h) return PQP_ERR_ALLOC;
+	h->d.N = N;
+	h->d.M = (Gp && Qp_inv && M > 0) ? M : 0;
+	h->o = o;
+	h->last_kernel = "none";
+	int rc = open_device(h, &o);
+	if (rc) { pqp_destroy(h); return rc; }
+	h->ldq = pqp_round_up(N, 32);
+	h->have_primal = h->d.M > 0;
+	if (h->have_primal) {
+		if ((rc = upload(h, &h->Gp, Gp, (size_t)N * M)) || (rc = upload(h, &h->Qp_inv, Qp_inv, (size_t)M * M))) {
+			pqp_destroy(h);
+			return rc;
+		}
+	}
+	if ((rc = dalloc(&h->Q, (size_t)N * h->ldq))) { pqp_destroy(h); return rc; }
+	cudaError_t e = cudaMemsetAsync(h->Q, 0, (size_t)N * h->ldq * sizeof(float), h->stream);
+	if (e == cudaSuccess)
+		e = cudaMemcpy2DAsync(h->Q, (size_t)h->ldq * sizeof(float), Qd, (size_t)N * sizeof(float), (size_t)N * sizeof(float), N,
+				      cudaMemcpyDefault, h->stream);
+	if (e != cudaSuccess) {
+		snprintf(g_cuda_err, sizeof g_cuda_err, "upload Qd -> %s", cudaGetErrorString(e));
+		pqp_destroy(h);
+		return PQP_ERR_CUDA;
+	}
+	if ((rc = finish_setup(h))) { pqp_destroy(h); return rc; }
+	*out = h;
+	return PQP_OK;
+}
+
+void pqp_destroy(pqp_handle *h)
+{
+	if (!h) return;
+	if (h->stream) {
+		cudaSetDevice(h->device);
+		cudaStreamSynchronize(h->stream);
+		if (h->l2_window_set) l2_persist_window(h, 0);
+	}
+	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
+			 h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
+			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf };
+	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
+		if (ptrs[i]) cudaFree(ptrs[i]);
+	if (h->ev0) cudaEventDestroy(h->ev0);
+	if (h->ev1) cudaEventDestroy(h->ev1);
+	if (h->stream) cudaStreamDestroy(h->stream);
+	cudaGetLastError();
+	free(h);
+}
+
+/* ---- the loop -------------------------------------------------------------------------------- */
+
+/* one problem: Fd (device, N), y0 (device N, or NULL -> y_init); result left in *y_res (device) */
+static int run_single(pqp_handle *h, const float *Fd, const float *Md, const float *y0, int iters, const float **y_res,
+		      pqp_status *st_dev, int want_status)
+{
+	const int N = h->d.N, ldq = h->ldq;
+	CK(cudaMemsetAsync(h->ybuf0, 0, (size_t)ldq * sizeof(float), h->stream));
+	CK(cudaMemsetAsync(h->ybuf1, 0, (size_t)ldq * sizeof(float), h->stream));
+	if (y0) {
+		CK(cudaMemcpyAsync(h->ybuf0, y0, (size_t)N * sizeof(float), cudaMemcpyDefault, h->stream));
+	} else {
+		CK(pqp_launch_fill(h->ybuf0, h->o.y_init, N, h->stream));
+		h->launches++;
+	}
+
+	pqp_gemv_args a;
+	memset(&a, 0, sizeof a);
+	a.Q = h->Q; a.QT = h->QT; a.ldq = ldq; a.N = N; a.theta = h->theta; a.Fd = Fd; a.Kp = h->Kp; a.Md = Md;
+	a.ybuf0 = h->ybuf0; a.ybuf1 = h->ybuf1; a.iters = iters; a.max_iters = h->o.max_iters;
+	a.check_every = h->o.check_every; a.erc = h->o.erc; a.eac = h->o.eac; a.eaj = h->o.eaj; a.erj = h->o.erj;
+	a.barrier = h->barrier; a.partials = h->partials; a.status = st_dev; a.result_buf = h->result_buf;
+	a.grid = h->gemv_grid; a.resident_rows = h->gemv_resident;
+
+	if (h->o.order == PQP_ORDER_STRICT) {
+		h->last_kernel = "gemv_strict";
+		float *bufs[2] = { h->ybuf0, h->ybuf1 };
+		int done = 0;
+		if (iters > 0) {
+			for (int k = 0; k < iters; k++) CK(pqp_launch_gemv_strict_step(&a, bufs[k & 1], bufs[(k + 1) & 1], h->stream));
+			h->launches += iters;
+			done = iters;
+			if (want_status) {
+				CK(pqp_launch_status(st_dev, h->Q, ldq, N, bufs[done & 1], ldq, Fd, Md, h->Kp, h->o.erc, h->o.eac, 1, done, h->stream));
+				h->launches++;
+			}
+		} else {
+			/* tolerance mode in reference order: test on the host every check_every updates */
+			pqp_status hs;
+			memset(&hs, 0, sizeof hs);
+			for (;;) {
+				CK(pqp_launch_status(st_dev, h->Q, ldq, N, bufs[done & 1], ldq, Fd, Md, h->Kp, h->o.erc, h->o.eac, 1, done, h->stream));
+				h->launches++;
+				CK(cudaMemcpyAsync(&hs, st_dev, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+				CK(cudaStreamSynchronize(h->stream));
+				const float tolc = h->o.eac; /* slack test: -g <= max(erc*Kp, eac) ~ eac-level here */
+				const int conv = hs.min_slack >= -tolc && fabsf(hs.gap) <= h->o.eaj && fabsf(hs.gap) <= h->o.erj * fabsf(hs.Jd);
+				if (conv || done >= h->o.max_iters) {
+					hs.converged = conv;
+					CK(cudaMemcpyAsync(st_dev, &hs, sizeof hs, cudaMemcpyHostToDevice, h->stream));
+					break;
+				}
+				for (int k = 0; k < h->o.check_every && done < h->o.max_iters; k++, done++)
+					CK(pqp_launch_gemv_strict_step(&a, bufs[done & 1], bufs[(done + 1) & 1], h->stream));
+				h->launches += h->o.check_every;
+			}
+		}
+		*y_res = bufs[done & 1];
+		return PQP_OK;
+	}
+
+	if (h->gemv_grid <= 0) return PQP_ERR_UNSUPPORTED;
+	h->last_kernel = h->gemv_resident > 0 ? "gemv_persistent_resident" : "gemv_persistent_stream";
+	CK(pqp_launch_gemv_persistent(&a, h->stream));
+	h->launches++;
+	/* which ping-pong buffer holds the result: known on the host for fixed counts */
+	if (iters > 0) {
+		*y_res = (iters & 1) ? h->ybuf1 : h->ybuf0;
+	} else {
+		int which = 0;
+		CK(cudaMemcpyAsync(&which, h->result_buf, sizeof which, cudaMemcpyDeviceToHost, h->stream));
+		CK(cudaStreamSynchronize(h->stream));
+		*y_res = which ? h->ybuf1 : h->ybuf0;
+	}
+	return PQP_OK;
+}
+
+static int ensure_batched_operands(pqp_handle *h)
+{
+	if (h->QpT) return PQP_OK;
+	const int N = h->d.N;
+	h->Kpad = pqp_round_up(N, PQP_BATCH_KPAD);
+	h->Ipad = pqp_round_up(N, PQP_BATCH_IPAD);
+	int rc;
+	if ((rc = dalloc(&h->QpT, (size_t)h->Kpad * h->Ipad)) || (rc = dalloc(&h->QnT, (size_t)h->Kpad * h->Ipad))) return rc;
+	CK(pqp_launch_build_split_t(h->QpT, h->QnT, h->Kpad, h->Ipad, h->Q, h->ldq, h->theta, N, h->stream));
+	h->launches++;
+	return PQP_OK;
+}
+
+/* Fd already in h->Fd [B x N]; Md in h->Md when want_status */
+static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, pqp_status *st)
+{
+	const int N = h->d.N;
+	const int strict = h->o.order == PQP_ORDER_STRICT;
+	const int want_status = st != NULL;
+	const float *Md = (want_status && h->have_fp_model) ? h->Md : NULL;
+	h->ev_valid = 0;
+
+	const int batched = B > 1 && iters > 0 && !strict && pqp_batched_simt_supported(N);
+	if (batched) {
+		int rc = ensure_batched_operands(h);
+		if (rc) return rc;
+		if (Y0) {
+			CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+		} else {
+			CK(pqp_launch_fill(h->Y, h->o.y_init, (size_t)B * N, h->stream));
+			h->launches++;
+		}
+		CK(cudaEventRecord(h->ev0, h->stream));
+		CK(pqp_launch_batched_simt_split(h->QpT, h->QnT, h->Kpad, h->Ipad, N, B, h->Fd, h->Y, iters, h->stream));
+		CK(cudaEventRecord(h->ev1, h->stream));
+		h->ev_valid = 1;
+		h->launches++;
+		h->last_kernel = "batched_simt";
+		if (want_status) {
+			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, Md, h->Kp, h->o.erc, h->o.eac, B, iters, h->stream));
+			h->launches++;
+		}
+	} else {
+		/* single-problem kernel, one problem after the other */
+		if (h->o.l2_persist && !strict && !h->l2_window_set && (size_t)N * h->ldq * sizeof(float) > (32u << 20)) {
+			int rc = l2_persist_window(h, 1);
+			if (rc) return rc;
+		}
+		CK(cudaEventRecord(h->ev0, h->stream));
+		for (int b = 0; b < B; b++) {
+			const float *y_res = NULL;
+			int rc = run_single(h, h->Fd + (size_t)b * N, Md ? Md + b : NULL, Y0 ? Y0 + (size_t)b * N : NULL, iters, &y_res,
+					    h->st + b, want_status);
+			if (rc) return rc;
+			CK(cudaMemcpyAsync(h->Y + (size_t)b * N, y_res, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+		}
+		CK(cudaEventRecord(h->ev1, h->stream));
+		h->ev_valid = 1;
+	}
+	if (Y) CK(cudaMemcpyAsync(Y, h->Y, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+	if (st) CK(cudaMemcpyAsync(st, h->st, (size_t)B * sizeof(pqp_status), cudaMemcpyDefault, h->stream));
+	return PQP_OK;
+}
+
+static int form_linear_terms(pqp_handle *h, const float *X, const float *D, int B, int want_status)
+{
+	const int M = h->d.M, N = h->d.N, nS = h->d.nState, nd = h->d.nDisH;
+	const int strict = h->o.order == PQP_ORDER_STRICT;
+	if (!h->have_fp_model) return PQP_ERR_INVALID;
+	if (nS > 0 && !X) return PQP_ERR_INVALID;
+	if (nS > 0) CK(cudaMemcpyAsync(h->X, X, (size_t)B * nS * sizeof(float), cudaMemcpyDefault, h->stream));
+	const float *Dd = h->D;
+	int Dstride = 0;
+	if (D && nd > 0) {
+		CK(cudaMemcpyAsync(h->Db, D, (size_t)B * nd * sizeof(float), cudaMemcpyDefault, h->stream));
+		Dd = h->Db;
+		Dstride = nd;
+	}
+	CK(pqp_launch_fp(h->Fp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, Dd, Dstride, h->X, B, M, nd, nS, h->stream));
+	CK(pqp_launch_fd(h->Fd, h->GQ, h->Fp, h->Kp, B, N, M, strict, h->stream));
+	h->launches += 2;
+	h->fp_B = B;
+	if (want_status) {
+		CK(pqp_launch_md(h->Md, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, Dd, Dstride, h->X, B, M,
+				 nd, nS, h->stream));
+		h->launches++;
+	}
+	return PQP_OK;
+}
+
+int pqp_solve_batch(pqp_handle *h, const float *X, const float *D, int B, int iters, const float *Y0, float *Y,
+		    pqp_status *st)
+{
+	if (!h || B <= 0) return PQP_ERR_INVALID;
+	CK(cudaSetDevice(h->device));
+	int rc = ensure_capacity(h, B);
+	if (rc) return rc;
+	if ((rc = form_linear_terms(h, X, D, B, st != NULL))) return rc;
+	if ((rc = run_loop(h, B, iters, Y0, Y, st))) return rc;
+	CK(cudaStreamSynchronize(h->stream));
+	return PQP_OK;
+}
+
+int pqp_solve_dual(pqp_handle *h, const float *Fd, int B, int iters, const float *Y0, float *Y, pqp_status *st)
+{
+	if (!h || B <= 0 || !Fd) return PQP_ERR_INVALID;
+	CK(cudaSetDevice(h->device));
+	int rc = ensure_capacity(h, B);
+	if (rc) return rc;
+	CK(cudaMemcpyAsync(h->Fd, Fd, (size_t)B * h->d.N * sizeof(float), cudaMemcpyDefault, h->stream));
+	h->fp_B = 0;
+	const int saved = h->have_fp_model;
+	h->have_fp_model = 0; /* no Md without Fp: Jd is reported without the constant */
+	rc = run_loop(h, B, iters, Y0, Y, st);
+	h->have_fp_model = saved;
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(h->stream));
+	return PQP_OK;
+}
+
+static int recover_on_device(pqp_handle *h, const float *Ydev, int ldy, const float *Fp, int B, float *U)
+{
+	const int M = h->d.M, N = h->d.N;
+	if (!h->have_primal || M <= 0) return PQP_ERR_INVALID;
+	if (Fp) {
+		CK(cudaMemcpyAsync(h->Fp, Fp, (size_t)B * M * sizeof(float), cudaMemcpyDefault, h->stream));
+		h->fp_B = B;
+	} else if (h->fp_B < B) {
+		return PQP_ERR_INVALID; /* no cached Fp for these problems */
+	}
+	CK(pqp_launch_recover(h->U, h->Tmp, Ydev, ldy, h->Fp, h->Gp, h->Qp_inv, B, N, M, h->o.order == PQP_ORDER_STRICT, h->stream));
+	h->launches += 2;
+	if (U) CK(cudaMemcpyAsync(U, h->U, (size_t)B * M * sizeof(float), cudaMemcpyDefault, h->stream));
+	return PQP_OK;
+}
+
+int pqp_recover_primal(pqp_handle *h, const float *Y, const float *Fp, int B, float *U)
+{
+	if (!h || !Y || !U || B <= 0) return PQP_ERR_INVALID;
+	CK(cudaSetDevice(h->device));
+	if (B > h->cap) {
+		/* growing the workspace would drop the cached Fp; only legal when the caller supplies Fp */
+		if (!Fp) return PQP_ERR_INVALID;
+		int rc = ensure_capacity(h, B);
+		if (rc) return rc;
+	}
+	CK(cudaMemcpyAsync(h->Y, Y, (size_t)B * h->d.N * sizeof(float), cudaMemcpyDefault, h->stream));
+	int rc = recover_on_device(h, h->Y, h->d.N, Fp, B, U);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(h->stream));
+	return PQP_OK;
+}
+
+int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B, int iters, const float *Y0, float *Y,
+			   float *U, pqp_status *st)
+{
+	if (!h || B <= 0 || !U) return PQP_ERR_INVALID;
+	CK(cudaSetDevice(h->device));
+	int rc = ensure_capacity(h, B);
+	if (rc) return rc;
+	if ((rc = form_linear_terms(h, X, D, B, st != NULL))) return rc;
+	if ((rc = run_loop(h, B, iters, Y0, Y, st))) return rc;
+	if ((rc = recover_on_device(h, h->Y, h->d.N, NULL, B, U))) return rc;
+	CK(cudaStreamSynchronize(h->stream));
+	return PQP_OK;
+}
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+int pqp_get_dual(pqp_handle *h, float *Qd, float *theta, float *GQ)
+{
+	if (!h) return PQP_ERR_INVALID;
+	CK(cudaSetDevice(h->device));
+	const int N = h->d.N, M = h->d.M;
+	if (Qd)
+		CK(cudaMemcpy2DAsync(Qd, (size_t)N * sizeof(float), h->Q, (size_t)h->ldq * sizeof(float), (size_t)N * sizeof(float), N,
+				     cudaMemcpyDefault, h->stream));
+	if (theta) CK(cudaMemcpyAsync(theta, h->theta, (size_t)N * sizeof(float), cudaMemcpyDefault, h->stream));
+	if (GQ) {
+		if (!h->GQ) return PQP_ERR_INVALID;
+		CK(cudaMemcpyAsync(GQ, h->GQ, (size_t)N * M * sizeof(float), cudaMemcpyDefault, h->stream));
+	}
+	CK(cudaStreamSynchronize(h->stream));
+	return PQP_OK;
+}
+
+int pqp_get_linear_terms(pqp_handle *h, int B, float *Fd, float *Fp)
+{
+	if (!h || B <= 0 || B > h->cap) return PQP_ERR_INVALID;
+	CK(cudaSetDevice(h->device));
+	if (Fd) CK(cudaMemcpyAsync(Fd, h->Fd, (size_t)B * h->d.N * sizeof(float), cudaMemcpyDefault, h->stream));
+	if (Fp) {
+		if (h->fp_B < B) return PQP_ERR_INVALID;
+		CK(cudaMemcpyAsync(Fp, h->Fp, (size_t)B * h->d.M * sizeof(float), cudaMemcpyDefault, h->stream));
+	}
+	CK(cudaStreamSynchronize(h->stream));
+	return PQP_OK;
+}
+
+void *pqp_get_stream(pqp_handle *h) { return h ? (void *)h->stream : NULL; }
+
+float pqp_last_solve_ms(pqp_handle *h)
+{
+	if (!h || !h->ev_valid) return -1.0f;
+	float ms = -1.0f;
+	if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
+	if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
+	return ms;
+}
+
+long long pqp_launch_count(pqp_handle *h) { return h ? h->launches : 0; }
+const char *pqp_last_kernel(pqp_handle *h) { return h ? h->last_kernel : "none"; }
+const float *pqp_device_qd(pqp_handle *h, int *ld)
+{
+	if (!h) return NULL;
+	if (ld) *ld = h->ldq;
+	return h->Q;
+}

@@ -1,0 +1,164 @@
+/*
+ * pqp_compat.c -- libpqp_compat.so: the reference's own function signatures, backed by
+ * libpqp_b200.so, so PQP_CPU.c's main() (or a test written like it) can link against the new
+ * solver unchanged.  Each function cites the reference definition it stands in for.
+ *
+ * The reference's functions return void and print-and-continue; these do the same: on a
+ * library error they print one line to stderr and leave the outputs untouched.  They are
+ * synchronous and take host pointers, as PQP_CPU.c passes them.  Sizes that the reference
+ * takes from #defines (computeFp, PQP_CPU.c:13-17) come from pqp_compat_set_dims().
+ *
+ * Order of arithmetic: pqp_compat_set_order(PQP_ORDER_STRICT) makes every result bit-identical
+ * to PQP_CPU.c; the default PQP_ORDER_FAST is within 1e-5 (normwise) of it.
+ */
+#include "pqp.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static pqp_dims g_dims = { 7, 28, 29, 1, 1, 7, 7, 1 }; /* PQP_CPU.c:13-17, 940-941 */
+static int g_order = PQP_ORDER_FAST;
+static long g_fixed_iters = 0; /* 0: run to the stop test like PQP_CPU.c:718 */
+static long g_last_h = 0;
+
+void pqp_compat_set_dims(int pHorizon, int nState, int nInput, int nOutput, int nDis)
+{
+	pqp_dims_mpc(&g_dims, pHorizon, nState, nInput, nOutput, nDis);
+}
+void pqp_compat_set_order(int order) { g_order = order; }
+/* > 0: solveQuadraticDual applies exactly this many updates (testing/CPU version/PQP_CPU_test.c:717) */
+void pqp_compat_set_fixed_iters(long k) { g_fixed_iters = k; }
+long pqp_compat_last_iterations(void) { return g_last_h; }
+
+static void complain(const char *fn, int rc)
+{
+	fprintf(stderr, "pqp_compat: %s failed: %s (%s)\n", fn, pqp_strerror(rc), pqp_last_cuda_error());
+}
+
+static pqp_opts opts_now(void)
+{
+	pqp_opts o;
+	pqp_default_opts(&o);
+	o.order = g_order;
+	o.check_every = 1;
+	return o;
+}
+
+/* PQP_CPU.c:373 */
+void computeFp(float *Fp, float *Fp1, float *Fp2, float *Fp3, float *D, float *x)
+{
+	/* M-vector: computed here on the host in the reference's own order (it is 3 tiny products) */
+	const int M = g_dims.M, nd = g_dims.nDisH, nS = g_dims.nState;
+	for (int i = 0; i < M; i++) {
+		float t1 = 0.0f, t2 = 0.0f;
+		for (int k = 0; k < nd; k++) t1 += Fp1[i * nd + k] * D[k];
+		for (int k = 0; k < nS; k++) t2 += Fp2[i * nS + k] * x[k];
+		Fp[i] = (t1 + t2) + (-1.0f * Fp3[i]);
+	}
+}
+
+/* PQP_CPU.c:489.  Qd/Fd/Md out; Qp_inv [M x M], Gp [N x M], Kp [N], Fp [M], Mp [1] in. */
+void convertToDual(float *Qd, float *Fd, float *Md, float *Qp_inv, float *Gp, float *Kp, float *Fp, float *Mp, int N, int M)
+{
+	pqp_dims d;
+	memset(&d, 0, sizeof d);
+	d.M = M;
+	d.N = N;
+	pqp_host_problem p;
+	memset(&p, 0, sizeof p);
+	p.Qp_inv = Qp_inv; p.Gp = Gp; p.Kp = Kp; p.Fp = Fp; p.Mp0 = Mp ? Mp[0] : 0.0f;
+	pqp_opts o = opts_now();
+	pqp_handle *h = NULL;
+	int rc = pqp_setup(&h, &d, &p, &o);
+	if (rc) { complain("convertToDual/pqp_setup", rc); return; }
+	rc = pqp_get_dual(h, Qd, NULL, NULL);
+	if (rc) complain("convertToDual/pqp_get_dual", rc);
+	/* Fd = GQ*Fp + Kp is formed by the solve entry point: run one update on a scratch y, read Fd back */
+	float *ytmp = (float *)malloc(sizeof(float) * (size_t)N);
+	pqp_status st;
+	rc = pqp_solve_batch(h, NULL, NULL, 1, 1, NULL, ytmp, &st);
+	if (rc) complain("convertToDual/pqp_solve_batch", rc);
+	else rc = pqp_get_linear_terms(h, 1, Fd, NULL);
+	if (rc) complain("convertToDual/pqp_get_linear_terms", rc);
+	free(ytmp);
+	if (Md) {
+		/* Md = Fp' Qp_inv Fp - Mp (PQP_CPU.c:472-479), reference order on the host: O(M^2) once */
+		float acc = 0.0f;
+		float *t = (float *)calloc((size_t)M, sizeof(float));
+		for (int j = 0; j < M; j++) {
+			float s = 0.0f;
+			for (int k = 0; k < M; k++) s += Fp[k] * Qp_inv[(size_t)k * M + j];
+			t[j] = s;
+		}
+		for (int j = 0; j < M; j++) acc += t[j] * Fp[j];
+		free(t);
+		Md[0] = acc - (Mp ? Mp[0] : 0.0f);
+	}
+	pqp_destroy(h);
+}
+
+/* PQP_CPU.c:694.  Y out [N], U out [M] (the last computeUfromY of terminate, PQP_CPU.c:675). */
+void solveQuadraticDual(float *Y, float *Qd, float *Fd, float *Md, float *U, float *Qp, float *Qp_inv, float *Fp,
+			float *Mp, float *Gp, float *Kp, int N, int M)
+{
+	(void)Qp; (void)Mp; (void)Kp; (void)Md;
+	pqp_opts o = opts_now();
+	pqp_handle *h = NULL;
+	int rc = pqp_setup_dual(&h, N, Qd, M, Gp, Qp_inv, &o);
+	if (rc) { complain("solveQuadraticDual/pqp_setup_dual", rc); return; }
+	pqp_status st;
+	memset(&st, 0, sizeof st);
+	rc = pqp_solve_dual(h, Fd, 1, (int)g_fixed_iters, NULL, Y, &st);
+	if (rc) complain("solveQuadraticDual/pqp_solve_dual", rc);
+	else if (U && Fp && Gp && Qp_inv) {
+		rc = pqp_recover_primal(h, Y, Fp, 1, U);
+		if (rc) complain("solveQuadraticDual/pqp_recover_primal", rc);
+	}
+	g_last_h = (long)st.iters + 1; /* the reference counts from 1 (PQP_CPU.c:714) */
+	printf("Printing number of iterations = %ld\n", g_last_h); /* PQP_CPU.c:741 */
+	pqp_destroy(h);
+}
+
+/* PQP_CPU.c:352 */
+void computeUfromY(float *U, float *Y, float *Fp, float *Gp, float *Qp_inv, int N, int M)
+{
+	/* a handle is built around a dual Hessian; recovery never reads it, so it gets N x N zeros */
+	pqp_opts o = opts_now();
+	pqp_handle *h = NULL;
+	float *Qz = (float *)calloc((size_t)N * N, sizeof(float));
+	if (!Qz) { complain("computeUfromY", PQP_ERR_ALLOC); return; }
+	int rc = pqp_setup_dual(&h, N, Qz, M, Gp, Qp_inv, &o);
+	free(Qz);
+	if (rc) { complain("computeUfromY/pqp_setup_dual", rc); return; }
+	rc = pqp_recover_primal(h, Y, Fp, 1, U);
+	if (rc) complain("computeUfromY/pqp_recover_primal", rc);
+	pqp_destroy(h);
+}
+
+/* PQP_CPU.c:648: J = 1/2 z'Qz + F'z + m/2.  O(n^2) scalar on the host, reference order. */
+float computeCost(float *Z, float *Q, float *F, float *M, int N)
+{
+	float J = 0;
+	float *t = (float *)calloc((size_t)N, sizeof(float));
+	for (int j = 0; j < N; j++) {
+		float s = 0.0f;
+		for (int k = 0; k < N; k++) s += Z[k] * Q[(size_t)k * N + j];
+		t[j] = s;
+	}
+	float q = 0.0f, l = 0.0f;
+	for (int j = 0; j < N; j++) q += t[j] * Z[j];
+	for (int j = 0; j < N; j++) l += F[j] * Z[j];
+	free(t);
+	J += 0.5 * q;
+	J += l;
+	J += M[0] / 2;
+	return J;
+}
+
+/*
+ * Not provided: updateY2 (PQP_CPU.c:603).  Its arguments are the two dense split matrices
+ * Qdp_theta / Qdn_theta, which this solver never materialises (one signed Qd + a theta vector);
+ * a single reference update is pqp_solve_dual(h, Fd, 1, 1, Y, Y_next, NULL).
+ */

@@ -1,0 +1,91 @@
+/*
+ * pqp_internal.h -- launcher prototypes shared by the .cu files of libpqp_b200.so.
+ * Nothing here is part of the public ABI (that is include/pqp.h).
+ */
+#ifndef PQP_INTERNAL_H
+#define PQP_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "pqp.h"
+
+#define PQP_GEMV_THREADS 512
+#define PQP_GEMV_WARPS (PQP_GEMV_THREADS / 32)
+
+static inline int pqp_round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+/* ---- setup kernels (pqp_setup_kernels.cu) ------------------------------------------------ */
+/* C[a x c] (ldc) = A[a x b] (lda) * op(B); transB: B stored [c x b] (ldb) else [b x c] (ldb).
+ * strict: one thread per element, k ascending, separately rounded mul/add (PQP_CPU.c:84-147). */
+cudaError_t pqp_launch_matmul_strict(float *C, int ldc, const float *A, int lda, const float *B, int ldb, int transB,
+				     int a, int b, int c, cudaStream_t s);
+/* fp32 SIMT tiled GEMM (FAST mode without tensor cores; also the cross-check for the tcgen05 path) */
+cudaError_t pqp_launch_matmul_simt(float *C, int ldc, const float *A, int lda, const float *B, int ldb, int transB,
+				   int a, int b, int c, cudaStream_t s);
+/* theta_i = max(sum_j max(0,-Q_ij), floor); strict: thread per row, j ascending */
+cudaError_t pqp_launch_theta(float *theta, const float *Q, int ldq, int N, float floor_, int strict, cudaStream_t s);
+/* out[c x r] (ldo) = in[r x c] (ldi) transposed */
+cudaError_t pqp_launch_transpose(float *out, int ldo, const float *in, int ldi, int r, int c, cudaStream_t s);
+
+/* ---- per-solve small kernels (pqp_setup_kernels.cu) --------------------------------------- */
+/* Fp[b] = Fp1*D[b] + Fp2*X[b] - Fp3, reference order (computeFp, PQP_CPU.c:373-382).  D_stride 0: shared D.
+ * nState == 0: Fp[b] = Fp_const. */
+cudaError_t pqp_launch_fp(float *Fp, const float *Fp1, const float *Fp2, const float *Fp3, const float *Fp_const,
+			  const float *D, int D_stride, const float *X, int B, int M, int nd, int nState,
+			  cudaStream_t s);
+/* Fd[b] = GQ*Fp[b] + Kp (computeFd, PQP_CPU.c:456-460); strict: k ascending per thread */
+cudaError_t pqp_launch_fd(float *Fd, const float *GQ, const float *Fp, const float *Kp, int B, int N, int M,
+			  int strict, cudaStream_t s);
+/* Md[b] = Fp' Qp_inv Fp - Mp(x_b) (computeMd PQP_CPU.c:472-479, computeMp :395-428); Mp1==NULL: Mp = Mp0 */
+cudaError_t pqp_launch_md(float *Md, const float *Fp, const float *Qp_inv, const float *Mp1, const float *Mp2,
+			  const float *Mp3, const float *Mp4, const float *Mp5, const float *Mp6, float Mp0,
+			  const float *D, int D_stride, const float *X, int B, int M, int nd, int nState, cudaStream_t s);
+/* U[b] = -(Qp_inv*(Gp'*Y[b] + Fp[b])) (computeUfromY, PQP_CPU.c:352-360); tmp [B x M] scratch */
+cudaError_t pqp_launch_recover(float *U, float *tmp, const float *Y, int ldy, const float *Fp, const float *Gp,
+			       const float *Qp_inv, int B, int N, int M, int strict, cudaStream_t s);
+/* fill n floats */
+cudaError_t pqp_launch_fill(float *p, float v, size_t n, cudaStream_t s);
+
+/* ---- single-problem iteration (pqp_gemv.cu) ------------------------------------------------- */
+typedef struct pqp_gemv_args {
+	const float *Q;     /* [N x ldq] signed Qd, padding columns zero */
+	const float *QT;    /* [N x ldq] transpose (strict mode only) */
+	int ldq, N;
+	const float *theta; /* [N] */
+	const float *Fd;    /* [N] */
+	const float *Kp;    /* [N] or NULL */
+	const float *Md;    /* [1] or NULL */
+	float *ybuf0, *ybuf1; /* [ldq] each, padding zero; ybuf0 holds y_0 */
+	int iters;          /* > 0: fixed count; <= 0: tolerance mode up to max_iters */
+	int max_iters, check_every;
+	float erc, eac, eaj, erj;
+	unsigned *barrier;  /* zeroed before launch */
+	float *partials;    /* [2][grid][8] */
+	pqp_status *status; /* device, 1 entry */
+	int *result_buf;    /* device int: which ybuf holds the answer */
+	int grid;           /* CTAs (cooperative, <= SM count) */
+	int resident_rows;  /* rows of each CTA's slab kept in shared memory across iterations */
+} pqp_gemv_args;
+
+cudaError_t pqp_gemv_smem_bytes(int N, int ldq, int grid, int resident_rows, size_t *bytes);
+cudaError_t pqp_launch_gemv_persistent(const pqp_gemv_args *a, cudaStream_t s);
+/* strict: one launch per iteration, thread i owns row i and walks k ascending over QT */
+cudaError_t pqp_launch_gemv_strict_step(const pqp_gemv_args *a, const float *y_in, float *y_out, cudaStream_t s);
+/* evaluation of the status quantities for one y (any mode) */
+cudaError_t pqp_launch_status(pqp_status *st, const float *Q, int ldq, int N, const float *Y, int ldy, const float *Fd,
+			      const float *Md, const float *Kp, float erc, float eac, int B, int iters, cudaStream_t s);
+
+/* ---- batched iteration (pqp_batched.cu) ------------------------------------------------------ */
+/* k-major pre-split operands: QpT/QnT [Kpad x Ipad], [k][i] = max(0,+-Qd[i][k]) + theta_i*(i==k) */
+cudaError_t pqp_launch_build_split_t(float *QpT, float *QnT, int Kpad, int Ipad, const float *Q, int ldq,
+				     const float *theta, int N, cudaStream_t s);
+/* iters updates of B problems, Y [B x N] in place, Fd [B x N]; fp32 SIMT */
+cudaError_t pqp_launch_batched_simt_split(const float *QpT, const float *QnT, int Kpad, int Ipad, int N, int B,
+					  const float *Fd, float *Y, int iters, cudaStream_t s);
+int pqp_batched_simt_supported(int N);
+#define PQP_BATCH_KPAD 16
+#define PQP_BATCH_IPAD 128
+
+#endif

@@ -1,0 +1,434 @@
+/*
+ * pqp_setup_kernels.cu -- the small kernels around the iteration loop (sm_100a).
+ *
+ *   matmul_strict / matmul_simt   convertToDual's products      PQP_CPU.c:489-498 (a3/a4 in SURVEY 8a)
+ *   theta                         computeTheta + diagonalAdd    PQP_CPU.c:503-519, 235-242 (a5)
+ *   fp / fd / md                  computeFp, computeFd, computeMd PQP_CPU.c:373-382, 456-460, 472-479 (a2/a3)
+ *   recover                       computeUfromY                 PQP_CPU.c:352-360 (a11)
+ *   status                        the quantities terminate() tests, PQP_CPU.c:673-687, from g = Qd y + Fd (a10)
+ *
+ * "strict" variants keep PQP_CPU.c's summation order (k ascending, separately rounded multiply
+ * and add via __fmul_rn/__fadd_rn, which nvcc never contracts) and are bit-identical to it.
+ */
+#include "pqp_internal.h"
+
+#define STRICT_TILE 32
+
+/* ---------------------------------------------------------------------------------------------
+ * C = A * op(B), reference order.  Classic 32x32 shared-memory tiling: tiles advance k ascending
+ * and each thread adds its tile's 32 products k ascending, so every output sees exactly the
+ * sequence  acc = fl(acc + fl(a_ik * b_kj)),  k = 0..b-1  of PQP_CPU.c:90-99.
+ * ------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(STRICT_TILE *STRICT_TILE)
+matmul_strict_kernel(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda,
+		     const float *__restrict__ B, int ldb, int transB, int a, int b, int c)
+{
+	__shared__ float As[STRICT_TILE][STRICT_TILE + 1];
+	__shared__ float Bs[STRICT_TILE][STRICT_TILE + 1]; /* Bs[k][j] */
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	const int i = blockIdx.y * STRICT_TILE + ty;
+	const int j = blockIdx.x * STRICT_TILE + tx;
+	float acc = 0.0f;
+	for (int k0 = 0; k0 < b; k0 += STRICT_TILE) {
+		const int ka = k0 + tx;
+		As[ty][tx] = (i < a && ka < b) ? A[(size_t)i * lda + ka] : 0.0f;
+		if (transB) {
+			/* B stored [c x b]: read row (blockIdx.x*32 + ty), column k0+tx, store transposed */
+			const int jr = blockIdx.x * STRICT_TILE + ty;
+			Bs[tx][ty] = (jr < c && ka < b) ? B[(size_t)jr * ldb + ka] : 0.0f;
+		} else {
+			const int kb = k0 + ty;
+			Bs[ty][tx] = (kb < b && j < c) ? B[(size_t)kb * ldb + j] : 0.0f;
+		}
+		__syncthreads();
+		const int kmax = min(STRICT_TILE, b - k0);
+		for (int k = 0; k < kmax; k++) acc = __fadd_rn(acc, __fmul_rn(As[ty][k], Bs[k][tx]));
+		__syncthreads();
+	}
+	if (i < a && j < c) C[(size_t)i * ldc + j] = acc;
+}
+
+cudaError_t pqp_launch_matmul_strict(float *C, int ldc, const float *A, int lda, const float *B, int ldb, int transB,
+				     int a, int b, int c, cudaStream_t s)
+{
+	dim3 block(STRICT_TILE, STRICT_TILE), grid((c + STRICT_TILE - 1) / STRICT_TILE, (a + STRICT_TILE - 1) / STRICT_TILE);
+	matmul_strict_kernel<<<grid, block, 0, s>>>(C, ldc, A, lda, B, ldb, transB, a, b, c);
+	return cudaGetLastError();
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * fp32 SIMT GEMM, 64x64 tile, 16-deep k slab, 4x4 outputs per thread.  FAST mode without tensor
+ * cores, and the cross-check of the tcgen05 path.
+ * ------------------------------------------------------------------------------------------- */
+#define SG_BM 64
+#define SG_BN 64
+#define SG_BK 16
+__global__ void __launch_bounds__(256)
+matmul_simt_kernel(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda, const float *__restrict__ B,
+		   int ldb, int transB, int a, int b, int c)
+{
+	__shared__ float As[SG_BK][SG_BM + 4]; /* As[k][i] */
+	__shared__ float Bs[SG_BK][SG_BN + 4]; /* Bs[k][j] */
+	const int tid = threadIdx.x;
+	const int tx = tid % 16, ty = tid / 16;
+	const int i0 = blockIdx.y * SG_BM, j0 = blockIdx.x * SG_BN;
+	float acc[4][4] = {};
+	for (int k0 = 0; k0 < b; k0 += SG_BK) {
+		/* A tile: 64 rows x 16 k; thread -> (row = tid/4, 4 consecutive k) */
+		{
+			const int r = tid / 4, kk = (tid % 4) * 4;
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int gi = i0 + r, gk = k0 + kk + u;
+				As[kk + u][r] = (gi < a && gk < b) ? A[(size_t)gi * lda + gk] : 0.0f;
+			}
+		}
+		if (transB) {
+			const int r = tid / 4, kk = (tid % 4) * 4;
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int gj = j0 + r, gk = k0 + kk + u;
+				Bs[kk + u][r] = (gj < c && gk < b) ? B[(size_t)gj * ldb + gk] : 0.0f;
+			}
+		} else {
+			const int kk = tid / 16, jj = (tid % 16) * 4;
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int gk = k0 + kk, gj = j0 + jj + u;
+				Bs[kk][jj + u] = (gk < b && gj < c) ? B[(size_t)gk * ldb + gj] : 0.0f;
+			}
+		}
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < SG_BK; k++) {
+			float av[4], bv[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				av[u] = As[k][ty * 4 + u];
+				bv[u] = Bs[k][tx * 4 + u];
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++)
+#pragma unroll
+				for (int v = 0; v < 4; v++) acc[u][v] = fmaf(av[u], bv[v], acc[u][v]);
+		}
+		__syncthreads();
+	}
+#pragma unroll
+	for (int u = 0; u < 4; u++)
+#pragma unroll
+		for (int v = 0; v < 4; v++) {
+			const int gi = i0 + ty * 4 + u, gj = j0 + tx * 4 + v;
+			if (gi < a && gj < c) C[(size_t)gi * ldc + gj] = acc[u][v];
+		}
+}
+
+cudaError_t pqp_launch_matmul_simt(float *C, int ldc, const float *A, int lda, const float *B, int ldb, int transB,
+				   int a, int b, int c, cudaStream_t s)
+{
+	dim3 grid((c + SG_BN - 1) / SG_BN, (a + SG_BM - 1) / SG_BM);
+	matmul_simt_kernel<<<grid, 256, 0, s>>>(C, ldc, A, lda, B, ldb, transB, a, b, c);
+	return cudaGetLastError();
+}
+
+/* out[c x r] = in[r x c]' through a padded 32x32 tile */
+__global__ void transpose_kernel(float *__restrict__ out, int ldo, const float *__restrict__ in, int ldi, int r, int c)
+{
+	__shared__ float t[32][33];
+	int x = blockIdx.x * 32 + threadIdx.x, y0 = blockIdx.y * 32;
+	for (int dy = threadIdx.y; dy < 32; dy += blockDim.y)
+		if (y0 + dy < r && x < c) t[dy][threadIdx.x] = in[(size_t)(y0 + dy) * ldi + x];
+	__syncthreads();
+	x = blockIdx.y * 32 + threadIdx.x; /* input row -> output column */
+	y0 = blockIdx.x * 32;             /* input column -> output row */
+	for (int dy = threadIdx.y; dy < 32; dy += blockDim.y)
+		if (y0 + dy < c && x < r) out[(size_t)(y0 + dy) * ldo + x] = t[threadIdx.x][dy];
+}
+
+cudaError_t pqp_launch_transpose(float *out, int ldo, const float *in, int ldi, int r, int c, cudaStream_t s)
+{
+	dim3 block(32, 8), grid((c + 31) / 32, (r + 31) / 32);
+	transpose_kernel<<<grid, block, 0, s>>>(out, ldo, in, ldi, r, c);
+	return cudaGetLastError();
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * theta.  strict: `Q` is the TRANSPOSE (so that thread i walking j ascending reads coalesced);
+ * fast: warp per row of Q with a shuffle tree.
+ * ------------------------------------------------------------------------------------------- */
+__global__ void theta_strict_kernel(float *__restrict__ theta, const float *__restrict__ QT, int ldq, int N, float floor_)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	float s = 0.0f;
+	for (int j = 0; j < N; j++) {
+		const float q = QT[(size_t)j * ldq + i];
+		const float qn = (0.0f > -q) ? 0.0f : -q; /* max(0.0,-q) of PQP_CPU.c:209 */
+		s = __fadd_rn(s, __fmul_rn(qn, 1.0f));
+	}
+	theta[i] = (s > floor_) ? s : floor_;
+}
+
+__global__ void theta_fast_kernel(float *__restrict__ theta, const float *__restrict__ Q, int ldq, int N, float floor_)
+{
+	const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+	if (row >= N) return;
+	const float4 *r4 = reinterpret_cast<const float4 *>(Q + (size_t)row * ldq);
+	float s = 0.0f;
+	for (int c = lane; c < ldq / 4; c += 32) {
+		const float4 q = r4[c];
+		s += fmaxf(-q.x, 0.0f) + fmaxf(-q.y, 0.0f) + fmaxf(-q.z, 0.0f) + fmaxf(-q.w, 0.0f);
+	}
+#pragma unroll
+	for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	if (lane == 0) theta[row] = fmaxf(s, floor_);
+}
+
+cudaError_t pqp_launch_theta(float *theta, const float *Q, int ldq, int N, float floor_, int strict, cudaStream_t s)
+{
+	if (strict)
+		theta_strict_kernel<<<(N + 127) / 128, 128, 0, s>>>(theta, Q, ldq, N, floor_);
+	else
+		theta_fast_kernel<<<(N + 7) / 8, 256, 0, s>>>(theta, Q, ldq, N, floor_);
+	return cudaGetLastError();
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Fp = Fp1*D + Fp2*x - Fp3 in the reference's order:  t1 = sum_k Fp1[i,k] D[k];  t2 = sum_k
+ * Fp2[i,k] x[k];  Fp = (t1 + 1*t2) + (-1*Fp3)   (PQP_CPU.c:375-379).  Always in this order:
+ * it is tiny, so FAST and STRICT share it and Fp is bit-identical to the reference in both.
+ * ------------------------------------------------------------------------------------------- */
+__global__ void fp_kernel(float *__restrict__ Fp, const float *__restrict__ Fp1, const float *__restrict__ Fp2,
+			  const float *__restrict__ Fp3, const float *__restrict__ Fp_const, const float *__restrict__ D,
+			  int D_stride, const float *__restrict__ X, int B, int M, int nd, int nState)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long long)B * M) return;
+	const int b = (int)(t / M), i = (int)(t % M);
+	if (nState == 0) {
+		Fp[t] = Fp_const[i];
+		return;
+	}
+	float t1 = 0.0f, t2 = 0.0f;
+	const float *d = D + (size_t)b * D_stride;
+	for (int k = 0; k < nd; k++) t1 = __fadd_rn(t1, __fmul_rn(Fp1[(size_t)i * nd + k], d[k]));
+	const float *x = X + (size_t)b * nState;
+	for (int k = 0; k < nState; k++) t2 = __fadd_rn(t2, __fmul_rn(Fp2[(size_t)i * nState + k], x[k]));
+	float f = __fadd_rn(t1, __fmul_rn(1.0f, t2));
+	f = __fadd_rn(f, __fmul_rn(-1.0f, Fp3[i]));
+	Fp[t] = f;
+}
+
+cudaError_t pqp_launch_fp(float *Fp, const float *Fp1, const float *Fp2, const float *Fp3, const float *Fp_const,
+			  const float *D, int D_stride, const float *X, int B, int M, int nd, int nState, cudaStream_t s)
+{
+	const long long n = (long long)B * M;
+	fp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(Fp, Fp1, Fp2, Fp3, Fp_const, D, D_stride, X, B, M, nd, nState);
+	return cudaGetLastError();
+}
+
+/* Fd = GQ*Fp + Kp.  Thread per (problem, row), k ascending: the reference's order (PQP_CPU.c:458-459). */
+__global__ void fd_seq_kernel(float *__restrict__ Fd, const float *__restrict__ GQ, const float *__restrict__ Fp,
+			      const float *__restrict__ Kp, int B, int N, int M)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long long)B * N) return;
+	const int b = (int)(t / N), i = (int)(t % N);
+	const float *g = GQ + (size_t)i * M, *f = Fp + (size_t)b * M;
+	float acc = 0.0f;
+	for (int k = 0; k < M; k++) acc = __fadd_rn(acc, __fmul_rn(g[k], f[k]));
+	Fd[t] = __fadd_rn(acc, __fmul_rn(1.0f, Kp[i]));
+}
+
+/* single problem, FAST: warp per row, coalesced, shuffle tree */
+__global__ void fd_warp_kernel(float *__restrict__ Fd, const float *__restrict__ GQ, const float *__restrict__ Fp,
+			       const float *__restrict__ Kp, int N, int M)
+{
+	const int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+	if (row >= N) return;
+	const float *g = GQ + (size_t)row * M;
+	float acc = 0.0f;
+	for (int k = lane; k < M; k += 32) acc = fmaf(g[k], Fp[k], acc);
+#pragma unroll
+	for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if (lane == 0) Fd[row] = acc + Kp[row];
+}
+
+cudaError_t pqp_launch_fd(float *Fd, const float *GQ, const float *Fp, const float *Kp, int B, int N, int M, int strict,
+			  cudaStream_t s)
+{
+	if (!strict && B == 1 && M >= 256) {
+		fd_warp_kernel<<<(N + 7) / 8, 256, 0, s>>>(Fd, GQ, Fp, Kp, N, M);
+	} else {
+		const long long n = (long long)B * N;
+		fd_seq_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(Fd, GQ, Fp, Kp, B, N, M);
+	}
+	return cudaGetLastError();
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Md = Fp' Qp_inv Fp - Mp(x), one block per problem.  Only shifts the reported dual cost, so the
+ * block-tree summation order (not the reference's) is within the status tolerance.
+ * ------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ float block_sum_256(float v, float *red)
+{
+#pragma unroll
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	__syncthreads();
+	if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = v;
+	__syncthreads();
+	float t = 0.0f;
+	for (int w = 0; w < (int)blockDim.x / 32; w++) t += red[w];
+	return t;
+}
+
+__global__ void __launch_bounds__(256)
+md_kernel(float *__restrict__ Md, const float *__restrict__ Fp, const float *__restrict__ Qp_inv,
+	  const float *__restrict__ Mp1, const float *__restrict__ Mp2, const float *__restrict__ Mp3,
+	  const float *__restrict__ Mp4, const float *__restrict__ Mp5, const float *__restrict__ Mp6, float Mp0,
+	  const float *__restrict__ D, int D_stride, const float *__restrict__ X, int M, int nd, int nState)
+{
+	__shared__ float red[8];
+	const int b = blockIdx.x;
+	const float *f = Fp + (size_t)b * M;
+	float part = 0.0f;
+	for (int j = threadIdx.x; j < M; j += blockDim.x) {
+		float tj = 0.0f;
+		for (int k = 0; k < M; k++) tj = fmaf(f[k], Qp_inv[(size_t)k * M + j], tj);
+		part = fmaf(tj, f[j], part);
+	}
+	const float quad = block_sum_256(part, red);
+	float mp = Mp0;
+	if (Mp1) {
+		const float *x = X + (size_t)b * nState, *d = D + (size_t)b * D_stride;
+		float p = 0.0f;
+		for (int j = threadIdx.x; j < nState; j += blockDim.x) {
+			float t1 = 0.0f, t2 = 0.0f;
+			for (int k = 0; k < nState; k++) t1 = fmaf(x[k], Mp1[(size_t)k * nState + j], t1);
+			for (int k = 0; k < nd; k++) t2 = fmaf(d[k], Mp2[(size_t)k * nState + j], t2);
+			p += 0.5f * (t1 + t2 + Mp4[j]) * x[j];
+		}
+		for (int j = threadIdx.x; j < nd; j += blockDim.x) {
+			float t3 = 0.0f;
+			for (int k = 0; k < nd; k++) t3 = fmaf(d[k], Mp3[(size_t)k * nd + j], t3);
+			p += 0.5f * (t3 + Mp5[j]) * d[j];
+		}
+		mp = block_sum_256(p, red) + 0.5f * Mp6[0];
+	}
+	if (threadIdx.x == 0) Md[b] = quad - mp;
+}
+
+cudaError_t pqp_launch_md(float *Md, const float *Fp, const float *Qp_inv, const float *Mp1, const float *Mp2,
+			  const float *Mp3, const float *Mp4, const float *Mp5, const float *Mp6, float Mp0, const float *D,
+			  int D_stride, const float *X, int B, int M, int nd, int nState, cudaStream_t s)
+{
+	md_kernel<<<B, 256, 0, s>>>(Md, Fp, Qp_inv, Mp1, Mp2, Mp3, Mp4, Mp5, Mp6, Mp0, D, D_stride, X, M, nd, nState);
+	return cudaGetLastError();
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Primal recovery U = -(Qp_inv (Gp' y + Fp)), reference order (PQP_CPU.c:355-358).
+ * Stage 1: tmp[b][i] = (sum_k Gp[k,i] y_k) + 1*Fp_i   (thread per (b,i): k ascending, coalesced over i)
+ * Stage 2: U[b][i]   = -(sum_k Qp_inv[i,k] tmp_k)
+ * ------------------------------------------------------------------------------------------- */
+__global__ void recover_stage1(float *__restrict__ tmp, const float *__restrict__ Y, int ldy, const float *__restrict__ Fp,
+			       const float *__restrict__ Gp, int B, int N, int M)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long long)B * M) return;
+	const int b = (int)(t / M), i = (int)(t % M);
+	const float *y = Y + (size_t)b * ldy;
+	float acc = 0.0f;
+	for (int k = 0; k < N; k++) acc = __fadd_rn(acc, __fmul_rn(Gp[(size_t)k * M + i], y[k]));
+	tmp[t] = __fadd_rn(acc, __fmul_rn(1.0f, Fp[t]));
+}
+__global__ void recover_stage2(float *__restrict__ U, const float *__restrict__ tmp, const float *__restrict__ Qp_inv, int B,
+			       int M)
+{
+	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (long long)B * M) return;
+	const int b = (int)(t / M), i = (int)(t % M);
+	const float *v = tmp + (size_t)b * M, *q = Qp_inv + (size_t)i * M;
+	float acc = 0.0f;
+	for (int k = 0; k < M; k++) acc = __fadd_rn(acc, __fmul_rn(q[k], v[k]));
+	U[t] = -acc;
+}
+
+cudaError_t pqp_launch_recover(float *U, float *tmp, const float *Y, int ldy, const float *Fp, const float *Gp,
+			       const float *Qp_inv, int B, int N, int M, int strict, cudaStream_t s)
+{
+	(void)strict; /* both modes use the reference order: the recovery is O(NM) once per solve */
+	const long long n = (long long)B * M;
+	const unsigned blocks = (unsigned)((n + 127) / 128);
+	recover_stage1<<<blocks, 128, 0, s>>>(tmp, Y, ldy, Fp, Gp, B, N, M);
+	recover_stage2<<<blocks, 128, 0, s>>>(U, tmp, Qp_inv, B, M);
+	return cudaGetLastError();
+}
+
+__global__ void fill_kernel(float *p, float v, size_t n)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t pqp_launch_fill(float *p, float v, size_t n, cudaStream_t s)
+{
+	if (n == 0) return cudaSuccess;
+	size_t blocks = (n + 255) / 256;
+	if (blocks > 148 * 8) blocks = 148 * 8;
+	fill_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, v, n);
+	return cudaGetLastError();
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Status of a given y: g = Qd y + Fd, then min g, y'g, Jd = sum y (g + Fd)/2 + Md/2, ||min(y,g)||inf.
+ * One block per problem; warps take rows round-robin.  (these replace the five GEMVs
+ * and four dot products of terminate(), PQP_CPU.c:673-687.)
+ * ------------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256)
+status_kernel(pqp_status *__restrict__ st, const float *__restrict__ Q, int ldq, int N, const float *__restrict__ Y, int ldy,
+	      const float *__restrict__ Fd, const float *__restrict__ Md, const float *__restrict__ Kp, float erc, float eac,
+	      int iters)
+{
+	__shared__ float r_min[8], r_gap[8], r_jd[8], r_kkt[8], r_viol[8];
+	const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+	const float *y = Y + (size_t)b * ldy, *fd = Fd + (size_t)b * N;
+	float vmin = INFINITY, gap = 0.0f, jd = 0.0f, kkt = 0.0f, viol = -INFINITY;
+	for (int i = warp; i < N; i += 8) {
+		const float *q = Q + (size_t)i * ldq;
+		float acc = 0.0f;
+		for (int k = lane; k < N; k += 32) acc = fmaf(q[k], y[k], acc);
+#pragma unroll
+		for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+		const float g = acc + fd[i], yi = y[i];
+		vmin = fminf(vmin, g);
+		gap = fmaf(yi, g, gap);
+		jd = fmaf(yi, 0.5f * (g + fd[i]), jd);
+		kkt = fmaxf(kkt, fabsf(fminf(yi, g)));
+		const float tol = Kp ? fmaxf(erc * Kp[i], eac) : eac;
+		viol = fmaxf(viol, -g - tol);
+	}
+	if (lane == 0) {
+		r_min[warp] = vmin; r_gap[warp] = gap; r_jd[warp] = jd; r_kkt[warp] = kkt; r_viol[warp] = viol;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < 8; w++) {
+			vmin = fminf(vmin, r_min[w]); gap += r_gap[w]; jd += r_jd[w];
+			kkt = fmaxf(kkt, r_kkt[w]); viol = fmaxf(viol, r_viol[w]);
+		}
+		pqp_status o;
+		o.iters = iters;
+		o.converged = 0;
+		o.min_slack = vmin;
+		o.gap = gap;
+		o.Jd = jd + (Md ? 0.5f * Md[b] : 0.0f);
+		o.kkt = kkt;
+		st[b] = o;
+	}
+}
+
+cudaError_t pqp_launch_status(pqp_status *st, const float *Q, int ldq, int N, const float *Y, int ldy, const float *Fd,
+			      const float *Md, const float *Kp, float erc, float eac, int B, int iters, cudaStream_t s)
+{
+	status_kernel<<<B, 256, 0, s>>>(st, Q, ldq, N, Y, ldy, Fd, Md, Kp, erc, eac, iters);
+	return cudaGetLastError();
+}

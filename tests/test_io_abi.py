@@ -1,0 +1,119 @@
+"""CPU tests of the host side: file formats, the seeded generator, and that libpqp_b200.so loads
+and exports every symbol include/pqp.h declares.  No compute call is made without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import EXAMPLE_DIR, GOLDEN, ROOT
+
+
+def test_library_exports_every_declared_symbol(pqp):
+    L = pqp.lib()
+    header = open(os.path.join(ROOT, "include", "pqp.h")).read()
+    declared = set(re.findall(r"\b(pqp_[a-z0-9_]+)\s*\(", header)) - {"pqp_error"}  # the enum name appears in prose
+    assert declared == set(pqp.ABI_SYMBOLS), declared ^ set(pqp.ABI_SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    compat = C.CDLL(pqp.COMPAT_PATH)
+    for name in ("convertToDual", "solveQuadraticDual", "computeUfromY", "computeFp", "computeCost",
+                 "pqp_compat_set_dims", "pqp_compat_set_order", "pqp_compat_set_fixed_iters"):
+        assert hasattr(compat, name), name
+
+
+def test_struct_layouts_match_header(pqp):
+    # sizes the C side reports via behaviour: defaults land in the right fields
+    o = pqp.default_opts()
+    assert (o.theta_floor, o.y_init) == (5.0, 1000.0)           # PQP_CPU.c:240, :710
+    assert abs(o.erc - 1e-6) < 1e-12 and abs(o.erj - 1e-6) < 1e-12  # PQP_CPU.c:19-22
+    assert o.order == pqp.ORDER_FAST and o.device == -1 and o.check_every >= 1
+    d = pqp.dims_mpc(**pqp.EXAMPLE_DIMS)
+    assert (d.M, d.N, d.nDisH) == (7, 28, 1)                     # PQP_CPU.c:940-941
+    d = pqp.dims_mpc(30, 12, 4, 4, 1)
+    assert (d.M, d.N) == (120, 480)                              # config C4
+    assert C.sizeof(pqp.Status) == pqp.STATUS_DTYPE.itemsize == 24
+
+
+def test_example_loader_matches_oracle_loader(pqp, oracle32):
+    got, d = pqp.load_example(EXAMPLE_DIR)
+    want = oracle32.load_example(EXAMPLE_DIR)
+    for k, v in want.items():
+        assert np.array_equal(got[k], v), k
+    # spot KATs of the column-major -> row-major transposition
+    assert got["Gp"].shape == (28, 7) and got["Gp"][0, 0] == 1.0 and got["Gp"][7, 0] == -1.0
+    assert np.all(got["Gp"][14:] == 0) and np.all(got["Kp"][:14] == 20.0) and np.all(got["Kp"][14:] == 0.0)
+    assert abs(got["Qp_inv"][0, 0] - 0.998114) < 1e-6 and abs(got["D"][0] - 312.15) < 1e-4
+
+
+def test_example_loader_errors(pqp, tmp_path):
+    with pytest.raises(pqp.PQPError) as e:
+        pqp.load_example(str(tmp_path))
+    assert e.value.code == -5
+    # truncated file -> IO error, not garbage
+    for f in os.listdir(EXAMPLE_DIR):
+        (tmp_path / f).write_text(open(os.path.join(EXAMPLE_DIR, f)).read())
+    (tmp_path / "Gp.txt").write_text("1.0 0.0 #")
+    with pytest.raises(pqp.PQPError):
+        pqp.load_example(str(tmp_path))
+
+
+def test_testfile_reader_is_literal(pqp):
+    prob, d = pqp.load_testfile(os.path.join(GOLDEN, "test2.txt"))
+    assert (d.M, d.N) == (100, 400)
+    tok = open(os.path.join(GOLDEN, "test2.txt")).read().split()
+    assert abs(prob["Qp_inv"][0, 0] - float(tok[2])) < 1e-6
+    assert np.count_nonzero(prob["Qp_inv"] - np.diag(np.diag(prob["Qp_inv"]))) == 0
+    assert set(np.unique(prob["Gp"])) == {-1.0, 0.0, 1.0}     # -1 stays -1 (reference reader maps it to +1)
+    kp_file = np.array(tok[2 + 100 + 100 + 1: 2 + 100 + 100 + 1 + 400], np.float32)
+    assert np.array_equal(prob["Kp"], kp_file)                 # Kp from the file (reference overwrites with rand())
+    gp_file = np.array(tok[2 + 100 + 100 + 1 + 400:], np.float32).reshape(400, 100)
+    assert np.array_equal(prob["Gp"], gp_file)
+
+
+def test_generator_is_seeded_and_roundtrips(pqp, tmp_path, gold_random):
+    a, d = pqp.generate_testproblem(101, 32, 64)
+    b, _ = pqp.generate_testproblem(101, 32, 64)
+    c, _ = pqp.generate_testproblem(102, 32, 64)
+    for k in ("Qp_inv", "Fp", "Kp", "Gp"):
+        assert np.array_equal(a[k], b[k]) and not np.array_equal(a[k], c[k])
+    # stable against the committed golden inputs
+    assert np.array_equal(np.diag(a["Qp_inv"]), gold_random["s101_Qp_inv_diag"])
+    assert np.array_equal(a["Gp"], gold_random["s101_Gp"].astype(np.float32))
+    # distribution of testing/test_generator.c:936-987
+    big, _ = pqp.generate_testproblem(7, 200, 600)
+    assert 0 <= big["Kp"].min() and big["Kp"].max() < 100 and 40 < big["Kp"].mean() < 60
+    frac = [(big["Gp"] == v).mean() for v in (-1, 0, 1)]
+    assert all(abs(f - 1 / 3) < 0.01 for f in frac)
+    path = str(tmp_path / "t.txt")
+    pqp.write_testfile(path, a, d)
+    r, d2 = pqp.load_testfile(path)
+    assert (d2.M, d2.N) == (32, 64)
+    for k in ("Qp_inv", "Fp", "Kp", "Gp"):
+        assert np.array_equal(a[k], r[k]), k
+    assert abs(a["Mp0"] - r["Mp0"]) < 1e-6
+
+
+def test_no_cpu_fallback(pqp):
+    """Without a B200 the solver refuses to compute (it must never silently run on the CPU)."""
+    if pqp.device_count() > 0:
+        pytest.skip("a GPU is present")
+    prob, d = pqp.load_example(EXAMPLE_DIR)
+    with pytest.raises(pqp.PQPError) as e:
+        pqp.Solver(d, prob)
+    assert e.value.code == -2
+    with pytest.raises(pqp.PQPError):
+        pqp.Solver(Qd=np.eye(4, dtype=np.float32))
+
+
+def test_product_never_references_the_oracle():
+    """The shipped sources must not include, link or import anything under oracle/."""
+    pkg = os.path.join(ROOT, "pqp-for-mpc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".c", ".cu", ".h", ".cuh", ".py")) or f == "Makefile":
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower(), (dirpath, f)
