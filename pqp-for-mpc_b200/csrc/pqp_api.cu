@@ -54,6 +54,7 @@ struct pqp_handle {
 	unsigned *barrier;
 	int *result_buf;
 	int gemv_grid, gemv_resident;
+	int tma_ok, tma_stages, tma_resident, tma_yc, tma_pinned;
 	int l2_window_set;
 	long long launches;
 	const char *last_kernel;
@@ -134,6 +135,15 @@ static int open_device(pqp_handle *h, const pqp_opts *opts)
 	int optin = 0;
 	CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 	h->smem_optin = (size_t)optin;
+	if (getenv("PQP_L2_CARVEOUT_MB")) {
+		/* experiment knob: size of the persisting-L2 carve-out (evict_last lines live there) */
+		int maxp = 0;
+		cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
+		size_t want = (size_t)atoi(getenv("PQP_L2_CARVEOUT_MB")) << 20;
+		if (want > (size_t)maxp) want = (size_t)maxp;
+		CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+		if (getenv("PQP_VERBOSE")) fprintf(stderr, "pqp: persisting L2 max %d MB, set %zu MB\n", maxp >> 20, want >> 20);
+	}
 	CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&h->ev0));
 	CK(cudaEventCreate(&h->ev1));
@@ -211,7 +221,48 @@ static int finish_setup(pqp_handle *h)
 		int v = atoi(env);
 		if (v >= 0 && v < res) res = v;
 	}
+	/* the LDG kernel only parks rows when the whole slab fits; partial residency belongs to the TMA kernel */
+	if (res < rows_max && !env) res = 0;
 	h->gemv_resident = res;
+
+	/* TMA-staged kernel: ring depth / residency / L2-pinned rows */
+	h->tma_ok = 0;
+	if (h->gemv_grid > 0) {
+		h->tma_ok = pqp_gemv_tma_plan(N, ldq, h->gemv_grid, budget, &h->tma_stages, &h->tma_resident, &h->tma_yc);
+		const char *e;
+		if ((e = getenv("PQP_GEMV_TMA")) && atoi(e) == 0) h->tma_ok = 0;
+		if (h->tma_ok) {
+			const int total = h->tma_stages + h->tma_resident;
+			if ((e = getenv("PQP_TMA_STAGES"))) {
+				int v = atoi(e);
+				if (v >= 2 && v <= total && h->tma_resident < rows_max) {
+					h->tma_stages = v;
+					h->tma_resident = total - v;
+				}
+			}
+			if ((e = getenv("PQP_TMA_RESIDENT"))) {
+				int v = atoi(e);
+				if (v >= 0 && v < h->tma_resident) h->tma_resident = v;
+			}
+			/* rows per slab fetched evict_last: ~80% of L2 spread evenly over the CTAs (only matters when Q > L2) */
+			int l2_bytes = 0;
+			cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, h->device);
+			h->tma_pinned = 0;
+			if (h->o.l2_persist && (size_t)N * ldq * sizeof(float) > (size_t)l2_bytes) {
+				/* measured (tools/gemv_sweep.py, N=8192): 64 MB carve-out + ~45% of L2 pinned is the best point */
+				h->tma_pinned = (int)(0.45 * (double)l2_bytes / ((double)h->gemv_grid * ldq * sizeof(float)));
+				int maxp = 0;
+				cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, h->device);
+				size_t want = (size_t)64 << 20;
+				if (want > (size_t)maxp) want = (size_t)maxp;
+				if (!getenv("PQP_L2_CARVEOUT_MB")) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+			}
+			if ((e = getenv("PQP_L2_PIN_ROWS"))) h->tma_pinned = atoi(e) > 0 ? atoi(e) : 0;
+			if (getenv("PQP_VERBOSE"))
+				fprintf(stderr, "pqp: gemv_tma N=%d grid=%d stages=%d resident=%d pinned=%d yc=%d\n", N, h->gemv_grid,
+					h->tma_stages, h->tma_resident, h->tma_pinned, h->tma_yc);
+		}
+	}
 
 	if ((rc = ensure_capacity(h, h->o.batch_capacity > 0 ? h->o.batch_capacity : 1))) return rc;
 	CK(cudaStreamSynchronize(h->stream));
@@ -435,8 +486,13 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 	}
 
 	if (h->gemv_grid <= 0) return PQP_ERR_UNSUPPORTED;
-	h->last_kernel = h->gemv_resident > 0 ? "gemv_persistent_resident" : "gemv_persistent_stream";
-	CK(pqp_launch_gemv_persistent(&a, h->stream));
+	if (iters > 0 && h->tma_ok) {
+		h->last_kernel = h->tma_resident >= (N + h->gemv_grid - 1) / h->gemv_grid + 1 ? "gemv_tma_resident" : "gemv_tma_stream";
+		CK(pqp_launch_gemv_tma(&a, h->tma_stages, h->tma_resident, h->tma_pinned, h->tma_yc, h->stream));
+	} else {
+		h->last_kernel = h->gemv_resident > 0 ? "gemv_persistent_resident" : "gemv_persistent_stream";
+		CK(pqp_launch_gemv_persistent(&a, h->stream));
+	}
 	h->launches++;
 	/* which ping-pong buffer holds the result: known on the host for fixed counts */
 	if (iters > 0) {
@@ -494,7 +550,7 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 		}
 	} else {
 		/* single-problem kernel, one problem after the other */
-		if (h->o.l2_persist && !strict && !h->l2_window_set && (size_t)N * h->ldq * sizeof(float) > (32u << 20)) {
+		if (h->o.l2_persist && getenv("PQP_L2_WINDOW") && !strict && !h->l2_window_set) {
 			int rc = l2_persist_window(h, 1);
 			if (rc) return rc;
 		}

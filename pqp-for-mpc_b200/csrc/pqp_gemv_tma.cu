@@ -1,0 +1,404 @@
+/*
+ * pqp_gemv_tma.cu -- single-problem PQP loop, TMA-staged (sm_100a).  The production path for
+ * fixed-count solves; pqp_gemv.cu's LDG kernel remains the general fallback (tolerance mode,
+ * rows too long for the ring).
+ *
+ * Same loop as pqp_gemv.cu (PQP_CPU.c:718-740 in one cooperative launch, one CTA per SM owning a
+ * slab of rows of the signed Qd), restructured around the TMA engine so that the HBM stream never
+ * stops -- not for the grid barrier, not for the y exchange, not for the update:
+ *
+ *   producer   warp 16, one elected thread: for every pass and every non-resident row of the slab,
+ *              waits for a free ring stage (mbarrier "empty"), arms the stage's "full" mbarrier with
+ *              the row's byte count and issues ONE cp.async.bulk (UBLKCP) global->shared copy of the
+ *              whole row (N*4 bytes) with an L2 cache-policy hint.  Q does not depend on y, so the
+ *              producer runs ahead across iteration boundaries: while the consumers sit in the grid
+ *              barrier the ring (S rows per SM, ~19 MB chip-wide) keeps HBM busy.
+ *   consumers  warps 0-15: each thread keeps ITS columns of y in registers (float4 x YC, reloaded
+ *              from L2 once per iteration), waits on "full", reads the row from shared memory with
+ *              conflict-free 128-bit loads, forms num += max(-q,0)*y, den += max(q,0)*y, releases
+ *              the stage ("empty"), warp-shuffles, and parks per-warp partials in shared memory.
+ *   finish     threads t < rows: fixed-order sum over the 16 warps, + theta_i*y_i + F-/F+, the
+ *              multiplicative update with IEEE division, y+ to the ping-pong vector, stop-test terms.
+ *   residency  the first R rows of every slab stay in shared memory for the whole launch (never
+ *              re-fetched); when the whole slab fits (N <= ~2.6k) the loop never touches HBM/L2 for Q.
+ *   L2 pinning the next P rows of every slab are fetched with an evict_last policy and the rest with
+ *              evict_first, so a fixed ~P/rows fraction of Q is served from the 126 MB L2 on every
+ *              iteration instead of HBM (Q at N=8192 is 268 MB: it cannot all stay).
+ *
+ * Summation order is IDENTICAL to pqp_gemv.cu (thread tid owns float4 columns tid+512u, u ascending;
+ * xor-shuffle 16..1; warps ascending), so both kernels return bit-identical y.
+ */
+#include "pqp_internal.h"
+
+#include <stdlib.h>
+
+#define CONSUMERS PQP_GEMV_THREADS /* 512 */
+#define TMA_THREADS (CONSUMERS + 32)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n\t"
+		".reg .pred p;\n\t"
+		"WAIT_LOOP:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra WAIT_DONE;\n\t"
+		"bra WAIT_LOOP;\n\t"
+		"WAIT_DONE:\n\t"
+		"}" ::"r"(smem_u32(bar)),
+		"r"(parity)
+		: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+			     smem_u32(dst)),
+		     "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+		     : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_last()
+{
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first()
+{
+	uint64_t p;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+	return p;
+}
+__device__ __forceinline__ uint64_t make_policy(int kind)
+{
+	uint64_t p;
+	switch (kind) {
+	case 1: asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); break;
+	case 2: asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); break;
+	case 3: asm volatile("createpolicy.fractional.L2::evict_unchanged.b64 %0, 1.0;" : "=l"(p)); break;
+	default: asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p)); break;
+	}
+	return p;
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory"); }
+
+__device__ __forceinline__ void grid_barrier_consumers(unsigned *counter, unsigned &target, unsigned nblocks)
+{
+	consumer_sync();
+	if (threadIdx.x == 0) {
+		target += nblocks;
+		__threadfence();
+		asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+		unsigned v;
+		do {
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+		} while ((int)(v - target) < 0);
+		__threadfence();
+	}
+	consumer_sync();
+}
+
+__device__ __forceinline__ void acc4t(float &num, float &den, const float4 q, const float4 y)
+{
+	den = fmaf(fmaxf(q.x, 0.0f), y.x, den);
+	num = fmaf(fmaxf(-q.x, 0.0f), y.x, num);
+	den = fmaf(fmaxf(q.y, 0.0f), y.y, den);
+	num = fmaf(fmaxf(-q.y, 0.0f), y.y, num);
+	den = fmaf(fmaxf(q.z, 0.0f), y.z, den);
+	num = fmaf(fmaxf(-q.z, 0.0f), y.z, num);
+	den = fmaf(fmaxf(q.w, 0.0f), y.w, den);
+	num = fmaf(fmaxf(-q.w, 0.0f), y.w, num);
+}
+
+struct TmaGeom {
+	int stages;     /* ring depth S */
+	int resident;   /* R rows per slab kept in shared memory */
+	int pinned;     /* P streamed rows per slab fetched evict_last */
+	int rows_max;
+	int pol_keep, pol_stream; /* 0 normal, 1 evict_first, 2 evict_last, 3 evict_unchanged */
+};
+
+/*
+ * Shared memory: ring [S][ldq] | resident [R][ldq] | part [2][16][rows_max] | red [16*8] | full[S], empty[S]
+ */
+template <int YC>
+__global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv_args a, const TmaGeom g)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+	const int N = a.N, ldq = a.ldq, n4 = ldq / 4;
+	const unsigned G = gridDim.x;
+	const int r0 = (int)((long long)N * blockIdx.x / G), r1 = (int)((long long)N * (blockIdx.x + 1) / G);
+	const int nrows = r1 - r0;
+	const int S = g.stages, R = min(g.resident, nrows), rows_max = g.rows_max;
+	const uint32_t row_bytes = (uint32_t)ldq * 4u;
+
+	float *ring = reinterpret_cast<float *>(smem_raw);
+	float *resid = ring + (size_t)S * ldq;
+	float *part = resid + (size_t)g.resident * ldq;
+	float *red = part + 2 * PQP_GEMV_WARPS * rows_max;
+	uint64_t *full = reinterpret_cast<uint64_t *>(red + PQP_GEMV_WARPS * 8);
+	uint64_t *empty = full + S;
+
+	const int passes = a.iters + 1; /* iters updates + one evaluation pass */
+
+	if (tid == 0) {
+		for (int s = 0; s < S; s++) {
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], PQP_GEMV_WARPS);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+
+	if (warp == PQP_GEMV_WARPS) {
+		/* ================= producer ================= */
+		if (lane == 0) {
+			const uint64_t pol_keep = make_policy(g.pol_keep), pol_stream = make_policy(g.pol_stream);
+			/* resident rows: one-time bulk copies, all on full[0]'s first phase */
+			long long idx = 0;
+			if (R > 0) {
+				mbar_arrive_expect_tx(&full[0], row_bytes * (uint32_t)R);
+				for (int t = 0; t < R; t++)
+					bulk_g2s(resid + (size_t)t * ldq, a.Q + (size_t)(r0 + t) * ldq, row_bytes, &full[0], pol_stream);
+				idx = 1; /* stage 0 / phase 0 is consumed by the residency handshake */
+			}
+			for (int p = 0; p < passes; p++) {
+				for (int t = R; t < nrows; t++, idx++) {
+					const int s = (int)(idx % S);
+					const uint32_t ph = (uint32_t)((idx / S) & 1);
+					mbar_wait(&empty[s], ph ^ 1u);
+					mbar_arrive_expect_tx(&full[s], row_bytes);
+					bulk_g2s(ring + (size_t)s * ldq, a.Q + (size_t)(r0 + t) * ldq, row_bytes, &full[s],
+						 (t - R) < g.pinned ? pol_keep : pol_stream);
+				}
+			}
+		}
+		return;
+	}
+
+	/* ================= consumers ================= */
+	long long idx = 0;
+	if (R > 0) {
+		mbar_wait(&full[0], 0);
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&empty[0]);
+		idx = 1;
+	}
+	/* per-row constants of the rows this thread finishes */
+	float th_r = 0.0f, fd_r = 0.0f, kp_tol = a.eac;
+	if (tid < nrows) {
+		th_r = a.theta[r0 + tid];
+		fd_r = a.Fd[r0 + tid];
+		if (a.Kp) kp_tol = fmaxf(a.erc * a.Kp[r0 + tid], a.eac);
+	}
+	unsigned bar_target = 0;
+
+	for (int p = 0; p < passes; p++) {
+		const float *y_in = (p & 1) ? a.ybuf1 : a.ybuf0;
+		float *y_out = (p & 1) ? a.ybuf0 : a.ybuf1;
+		const bool is_last = (p == passes - 1);
+
+		float4 yv[YC];
+#pragma unroll
+		for (int u = 0; u < YC; u++) {
+			const int c = tid + u * CONSUMERS;
+			yv[u] = (c < n4) ? __ldcg(reinterpret_cast<const float4 *>(y_in) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+		const float y_mine = (tid < nrows) ? __ldcg(y_in + r0 + tid) : 0.0f;
+
+		for (int t = 0; t < nrows; t++) {
+			const float4 *src;
+			int s = 0;
+			if (t < R) {
+				src = reinterpret_cast<const float4 *>(resid + (size_t)t * ldq);
+			} else {
+				s = (int)(idx % S);
+				mbar_wait(&full[s], (uint32_t)((idx / S) & 1));
+				src = reinterpret_cast<const float4 *>(ring + (size_t)s * ldq);
+			}
+			float num = 0.0f, den = 0.0f;
+			float4 q[YC];
+#pragma unroll
+			for (int u = 0; u < YC; u++) {
+				const int c = tid + u * CONSUMERS;
+				q[u] = (c < n4) ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+			if (t >= R) {
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&empty[s]); /* the row is in registers: hand the stage back */
+				idx++;
+			}
+#pragma unroll
+			for (int u = 0; u < YC; u++) acc4t(num, den, q[u], yv[u]);
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				num += __shfl_xor_sync(0xffffffffu, num, o);
+				den += __shfl_xor_sync(0xffffffffu, den, o);
+			}
+			if (lane == 0) {
+				part[(0 * PQP_GEMV_WARPS + warp) * rows_max + t] = num;
+				part[(1 * PQP_GEMV_WARPS + warp) * rows_max + t] = den;
+			}
+		}
+		consumer_sync();
+
+		float e_min = INFINITY, e_gap = 0.0f, e_jd = 0.0f, e_kkt = 0.0f, e_viol = -INFINITY;
+		if (tid < nrows) {
+			float num = 0.0f, den = 0.0f;
+#pragma unroll
+			for (int w = 0; w < PQP_GEMV_WARPS; w++) {
+				num += part[(0 * PQP_GEMV_WARPS + w) * rows_max + tid];
+				den += part[(1 * PQP_GEMV_WARPS + w) * rows_max + tid];
+			}
+			num = fmaf(th_r, y_mine, num) + fmaxf(-fd_r, 0.0f);
+			den = fmaf(th_r, y_mine, den) + fmaxf(fd_r, 0.0f);
+			if (!is_last) y_out[r0 + tid] = __fdiv_rn(num, den) * y_mine;
+			if (is_last) {
+				const float gq = den - num;
+				e_min = gq;
+				e_gap = y_mine * gq;
+				e_jd = y_mine * (0.5f * (gq + fd_r));
+				e_kkt = fabsf(fminf(y_mine, gq));
+				e_viol = -gq - kp_tol;
+			}
+		}
+		if (is_last) {
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				e_min = fminf(e_min, __shfl_xor_sync(0xffffffffu, e_min, o));
+				e_gap += __shfl_xor_sync(0xffffffffu, e_gap, o);
+				e_jd += __shfl_xor_sync(0xffffffffu, e_jd, o);
+				e_kkt = fmaxf(e_kkt, __shfl_xor_sync(0xffffffffu, e_kkt, o));
+				e_viol = fmaxf(e_viol, __shfl_xor_sync(0xffffffffu, e_viol, o));
+			}
+			if (lane == 0) {
+				red[warp * 8 + 0] = e_min; red[warp * 8 + 1] = e_gap; red[warp * 8 + 2] = e_jd;
+				red[warp * 8 + 3] = e_kkt; red[warp * 8 + 4] = e_viol;
+			}
+			consumer_sync();
+			if (tid == 0) {
+				for (int w = 1; w < PQP_GEMV_WARPS; w++) {
+					e_min = fminf(e_min, red[w * 8 + 0]); e_gap += red[w * 8 + 1]; e_jd += red[w * 8 + 2];
+					e_kkt = fmaxf(e_kkt, red[w * 8 + 3]); e_viol = fmaxf(e_viol, red[w * 8 + 4]);
+				}
+				float *slot = a.partials + (size_t)blockIdx.x * 8;
+				slot[0] = e_min; slot[1] = e_gap; slot[2] = e_jd; slot[3] = e_kkt; slot[4] = e_viol;
+			}
+		}
+
+		grid_barrier_consumers(a.barrier, bar_target, G);
+
+		if (is_last && blockIdx.x == 0 && warp == 0) {
+			float v_min = INFINITY, v_gap = 0.0f, v_jd = 0.0f, v_kkt = 0.0f;
+			for (unsigned c = lane; c < G; c += 32) {
+				const float *sl = a.partials + (size_t)c * 8;
+				v_min = fminf(v_min, __ldcg(sl + 0)); v_gap += __ldcg(sl + 1); v_jd += __ldcg(sl + 2);
+				v_kkt = fmaxf(v_kkt, __ldcg(sl + 3));
+			}
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				v_min = fminf(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
+				v_gap += __shfl_xor_sync(0xffffffffu, v_gap, o);
+				v_jd += __shfl_xor_sync(0xffffffffu, v_jd, o);
+				v_kkt = fmaxf(v_kkt, __shfl_xor_sync(0xffffffffu, v_kkt, o));
+			}
+			if (lane == 0) {
+				pqp_status o;
+				o.iters = a.iters;
+				o.converged = 0;
+				o.min_slack = v_min;
+				o.gap = v_gap;
+				o.Jd = v_jd + (a.Md ? 0.5f * a.Md[0] : 0.0f);
+				o.kkt = v_kkt;
+				*a.status = o;
+				*a.result_buf = p & 1;
+			}
+		}
+	}
+}
+
+static size_t tma_smem_bytes(int ldq, const TmaGeom &g)
+{
+	return sizeof(float) * ((size_t)(g.stages + g.resident) * ldq + 2 * PQP_GEMV_WARPS * (size_t)g.rows_max + PQP_GEMV_WARPS * 8) +
+	       sizeof(uint64_t) * 2 * (size_t)g.stages;
+}
+
+/* picks ring depth / residency for the shared-memory budget; returns 0 when the shape does not fit this kernel */
+int pqp_gemv_tma_plan(int N, int ldq, int grid, size_t smem_budget, int *stages, int *resident, int *yc)
+{
+	const int n4 = ldq / 4;
+	int YC = (n4 + CONSUMERS - 1) / CONSUMERS;
+	if (YC > 8) return 0;
+	YC = YC <= 1 ? 1 : (YC <= 2 ? 2 : (YC <= 4 ? 4 : 8));
+	const int rows_max = (N + grid - 1) / grid + 1;
+	if (rows_max > CONSUMERS) return 0;
+	TmaGeom g;
+	g.rows_max = rows_max;
+	g.pinned = 0;
+	/* whole slab resident if it fits (then a token ring of 1), else the deepest ring up to 6 with the rest resident */
+	g.stages = 1;
+	g.resident = rows_max;
+	if (tma_smem_bytes(ldq, g) <= smem_budget) {
+		*stages = 1; *resident = rows_max; *yc = YC;
+		return 1;
+	}
+	const size_t row = (size_t)ldq * sizeof(float);
+	g.resident = 0;
+	g.stages = 0;
+	const size_t fixed = tma_smem_bytes(ldq, g);
+	if (fixed + 2 * row + 64 > smem_budget) return 0;
+	int total_rows = (int)((smem_budget - fixed - 128) / (row + 16));
+	/* ring depth by BYTES in flight: one SM needs ~100 KB outstanding to cover the HBM latency at its share of
+	 * the bandwidth (measured: 3 x 32 KB rows is as fast as 4; 4 x 16 KB rows is not enough) */
+	int S = (int)((96 * 1024 + row - 1) / row);
+	if (S < 3) S = 3;
+	if (S > total_rows) S = total_rows;
+	if (S < 2) return 0;
+	*stages = S;
+	*resident = total_rows - S;
+	*yc = YC;
+	return 1;
+}
+
+cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident, int pinned, int yc, cudaStream_t s)
+{
+	TmaGeom g;
+	g.stages = stages;
+	g.resident = resident;
+	g.pinned = pinned;
+	g.rows_max = (a->N + a->grid - 1) / a->grid + 1;
+	g.pol_keep = 2;
+	g.pol_stream = 1;
+	if (getenv("PQP_POL_KEEP")) g.pol_keep = atoi(getenv("PQP_POL_KEEP"));
+	if (getenv("PQP_POL_STREAM")) g.pol_stream = atoi(getenv("PQP_POL_STREAM"));
+	const size_t smem = tma_smem_bytes(a->ldq, g);
+	const void *fn = NULL;
+	switch (yc) {
+	case 1: fn = (const void *)gemv_tma_kernel<1>; break;
+	case 2: fn = (const void *)gemv_tma_kernel<2>; break;
+	case 4: fn = (const void *)gemv_tma_kernel<4>; break;
+	case 8: fn = (const void *)gemv_tma_kernel<8>; break;
+	default: return cudaErrorInvalidValue;
+	}
+	cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	e = cudaMemsetAsync(a->barrier, 0, sizeof(unsigned), s);
+	if (e != cudaSuccess) return e;
+	pqp_gemv_args args = *a;
+	void *params[] = { (void *)&args, (void *)&g };
+	return cudaLaunchCooperativeKernel(fn, dim3(a->grid), dim3(TMA_THREADS), params, smem, s);
+}

@@ -71,6 +71,9 @@ typedef struct pqp_gemv_args {
 
 cudaError_t pqp_gemv_smem_bytes(int N, int ldq, int grid, int resident_rows, size_t *bytes);
 cudaError_t pqp_launch_gemv_persistent(const pqp_gemv_args *a, cudaStream_t s);
+/* TMA-staged variant (pqp_gemv_tma.cu), fixed-count solves */
+int pqp_gemv_tma_plan(int N, int ldq, int grid, size_t smem_budget, int *stages, int *resident, int *yc);
+cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident, int pinned, int yc, cudaStream_t s);
 /* strict: one launch per iteration, thread i owns row i and walks k ascending over QT */
 cudaError_t pqp_launch_gemv_strict_step(const pqp_gemv_args *a, const float *y_in, float *y_out, cudaStream_t s);
 /* evaluation of the status quantities for one y (any mode) */
