@@ -249,8 +249,8 @@ static int finish_setup(pqp_handle *h)
 			cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, h->device);
 			h->tma_pinned = 0;
 			if (h->o.l2_persist && (size_t)N * ldq * sizeof(float) > (size_t)l2_bytes) {
-				/* measured (tools/gemv_sweep.py, N=8192): 64 MB carve-out + ~45% of L2 pinned is the best point */
-				h->tma_pinned = (int)(0.45 * (double)l2_bytes / ((double)h->gemv_grid * ldq * sizeof(float)));
+				/* measured (tools/gemv_sweep.py, N=8192): 64 MB carve-out + ~60% of L2 pinned (16 rows/slab) is the best point */
+				h->tma_pinned = (int)(0.6 * (double)l2_bytes / ((double)h->gemv_grid * ldq * sizeof(float)));
 				int maxp = 0;
 				cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, h->device);
 				size_t want = (size_t)64 << 20;

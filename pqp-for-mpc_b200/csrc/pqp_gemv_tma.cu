@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 					bulk_g2s(resid + (size_t)t * ldq, a.Q + (size_t)(r0 + t) * ldq, row_bytes, &full[0], pol_stream);
 				idx = 1; /* stage 0 / phase 0 is consumed by the residency handshake */
 			}
+			const int T = max(nrows - R, 1), P = min(g.pinned, T);
 			for (int p = 0; p < passes; p++) {
 				for (int t = R; t < nrows; t++, idx++) {
 					const int s = (int)(idx % S);
@@ -183,7 +184,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 					mbar_wait(&empty[s], ph ^ 1u);
 					mbar_arrive_expect_tx(&full[s], row_bytes);
 					bulk_g2s(ring + (size_t)s * ldq, a.Q + (size_t)(r0 + t) * ldq, row_bytes, &full[s],
-						 (t - R) < g.pinned ? pol_keep : pol_stream);
+						 /* pinned rows are spread evenly through the slab so L2 hits and HBM misses overlap in time */
+						 (((long long)(t - R + 1) * P) / T != ((long long)(t - R) * P) / T) ? pol_keep : pol_stream);
 				}
 			}
 		}
@@ -363,8 +365,8 @@ int pqp_gemv_tma_plan(int N, int ldq, int grid, size_t smem_budget, int *stages,
 	if (fixed + 2 * row + 64 > smem_budget) return 0;
 	int total_rows = (int)((smem_budget - fixed - 128) / (row + 16));
 	/* ring depth by BYTES in flight: one SM needs ~100 KB outstanding to cover the HBM latency at its share of
-	 * the bandwidth (measured: 3 x 32 KB rows is as fast as 4; 4 x 16 KB rows is not enough) */
-	int S = (int)((96 * 1024 + row - 1) / row);
+	 * the bandwidth (measured at N=8192 with L2 pinning on: 4 x 32 KB rows beat 3 and 6) */
+	int S = (int)((128 * 1024 + row - 1) / row);
 	if (S < 3) S = 3;
 	if (S > total_rows) S = total_rows;
 	if (S < 2) return 0;
