@@ -95,7 +95,8 @@ typedef struct pqp_opts {
 	int max_iters;     /* cap for run-to-tolerance mode                         default 100000 */
 	int check_every;   /* run-to-tolerance: test every this many iterations     default 8    */
 	int batch_capacity;/* problems the workspace is sized for (grows on demand) default 1    */
-	int use_tensor_cores; /* 1: tcgen05 3xTF32 for setup GEMMs / batched loop in FAST; 0: fp32 SIMT. default 1 */
+	int use_tensor_cores; /* FAST mode: 0 fp32 SIMT everywhere; 1 (default) tcgen05 3xTF32 for the setup GEMMs;
+			       * 2 also the batched loop on tcgen05 (faster, but above the 1e-5 parity tolerance: opt-in) */
 	int l2_persist;    /* 1: pin as much of Q as the device allows in L2 (GEMV regime) default 1 */
 } pqp_opts;
 
@@ -185,6 +186,15 @@ int pqp_recover_primal(pqp_handle *h, const float *Y, const float *Fp, int B, fl
 /* pqp_solve_batch followed by pqp_recover_primal on the device-resident Y (one stream, no host sync between). */
 int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B, int iters, const float *Y0,
 			   float *Y, float *U, pqp_status *st);
+
+/*
+ * out[a x c] = op(A)[a x b] * op(B)[b x c] on the GPU: the reference's matrixMultiply (PQP_CPU.c:84-147) with its
+ * transpose flags (tA: A is stored [b x a]; tB: B is stored [c x b]).  engine: PQP_MM_STRICT = the reference's
+ * summation order, bit-identical; PQP_MM_SIMT = fp32 FMA tiles; PQP_MM_TENSOR = tcgen05 3xTF32 (fp32-level accuracy).
+ * All pointers host or device; device < 0 = current.
+ */
+enum { PQP_MM_STRICT = 0, PQP_MM_SIMT = 1, PQP_MM_TENSOR = 2 };
+int pqp_matmul(float *out, const float *A, int tA, const float *B, int tB, int a, int b, int c, int engine, int device);
 
 /* ---- introspection (tests, benches) ----------------------------------------------------- */
 /* copies out what setup built; any pointer may be NULL.  Qd [N x N], theta [N], GQ [N x M] (host buffers) */

@@ -69,8 +69,9 @@ ABI_SYMBOLS = (
     "pqp_load_example", "pqp_load_testfile", "pqp_generate_testproblem", "pqp_write_testfile", "pqp_free_problem",
     "pqp_setup", "pqp_setup_dual", "pqp_destroy", "pqp_solve_batch", "pqp_solve_dual", "pqp_recover_primal",
     "pqp_solve_batch_primal", "pqp_get_dual", "pqp_get_linear_terms", "pqp_get_stream", "pqp_last_solve_ms",
-    "pqp_launch_count", "pqp_last_kernel", "pqp_device_qd",
+    "pqp_launch_count", "pqp_last_kernel", "pqp_device_qd", "pqp_matmul",
 )
+MM_STRICT, MM_SIMT, MM_TENSOR = 0, 1, 2
 
 
 class PQPError(RuntimeError):
@@ -229,6 +230,20 @@ def _as_ptr(a):
     if isinstance(a, (int, np.integer)):
         return C.c_void_p(int(a))
     return a.ctypes.data_as(C.c_void_p)
+
+
+def matmul(A, B, tA=False, tB=False, engine=MM_TENSOR, device=-1):
+    """pqp_matmul: the reference's matrixMultiply (PQP_CPU.c:84-147) on the GPU.  A, B as stored (see tA/tB)."""
+    A = np.ascontiguousarray(A, np.float32)
+    B = np.ascontiguousarray(B, np.float32)
+    a, b = (A.shape[1], A.shape[0]) if tA else A.shape
+    c = B.shape[0] if tB else B.shape[1]
+    assert (B.shape[1] if tB else B.shape[0]) == b
+    out = np.empty((a, c), np.float32)
+    rc = lib().pqp_matmul(_as_ptr(out), _as_ptr(A), int(tA), _as_ptr(B), int(tB), a, b, c, int(engine), int(device))
+    if rc:
+        raise PQPError(rc, "pqp_matmul")
+    return out
 
 
 class Solver:

@@ -43,6 +43,7 @@ struct pqp_handle {
 	float *Mp1, *Mp2, *Mp3, *Mp4, *Mp5, *Mp6;
 	float Mp0;
 	float *QpT, *QnT; /* batched operands, built on first batched solve */
+	void *umma_tiles; /* pre-split, pre-tiled tf32 hi/lo operand of the tcgen05 batched kernel */
 	int Kpad, Ipad;
 	/* per-batch workspace */
 	int cap;
@@ -348,6 +349,16 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 		if (strict) {
 			e = pqp_launch_matmul_strict(h->GQ, M, h->Gp, M, h->Qp_inv, M, 0, N, M, M, h->stream);
 			if (e == cudaSuccess) e = pqp_launch_matmul_strict(h->Q, h->ldq, h->GQ, M, h->Gp, M, 1, N, M, N, h->stream);
+		} else if (o.use_tensor_cores && N >= 64 && M >= 32) {
+			/* tcgen05 3xTF32: both operands K-major, so Qp_inv goes in transposed */
+			float *QiT = NULL;
+			if ((rc = dalloc(&QiT, (size_t)M * M))) { pqp_destroy(h); return rc; }
+			e = pqp_launch_transpose(QiT, M, h->Qp_inv, M, M, M, h->stream);
+			if (e == cudaSuccess) e = pqp_launch_gemm_umma(h->GQ, M, h->Gp, M, QiT, M, N, M, M, h->stream);
+			if (e == cudaSuccess) e = pqp_launch_gemm_umma(h->Q, h->ldq, h->GQ, M, h->Gp, M, N, M, N, h->stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+			cudaFree(QiT);
+			h->launches += 1;
 		} else {
 			e = pqp_launch_matmul_simt(h->GQ, M, h->Gp, M, h->Qp_inv, M, 0, N, M, M, h->stream);
 			if (e == cudaSuccess) e = pqp_launch_matmul_simt(h->Q, h->ldq, h->GQ, M, h->Gp, M, 1, N, M, N, h->stream);
@@ -413,7 +424,7 @@ void pqp_destroy(pqp_handle *h)
 		if (h->l2_window_set) l2_persist_window(h, 0);
 	}
 	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
-			 h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
+			 h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
 			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf };
 	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
 		if (ptrs[i]) cudaFree(ptrs[i]);
@@ -506,6 +517,28 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 	return PQP_OK;
 }
 
+static int use_umma_batched(const pqp_handle *h)
+{
+	/* opt-in (use_tensor_cores >= 2 or PQP_BATCHED_UMMA=1): the tensor core's truncating accumulation leaves the
+	 * 3xTF32 loop ~5-100x above the fp32 noise floor after 1000 updates, so the parity-clean fp32
+	 * SIMT kernel stays the default batched path */
+	const char *e = getenv("PQP_BATCHED_UMMA");
+	if (e) return atoi(e) != 0 && pqp_batched_umma_supported(h->d.N);
+	return h->o.use_tensor_cores >= 2 && pqp_batched_umma_supported(h->d.N);
+}
+
+static int ensure_umma_tiles(pqp_handle *h)
+{
+	if (h->umma_tiles) return PQP_OK;
+	unsigned char *t = NULL;
+	int rc = dalloc(&t, pqp_batched_umma_tiles_bytes(h->d.N));
+	if (rc) return rc;
+	h->umma_tiles = t;
+	CK(pqp_launch_build_umma_tiles(h->umma_tiles, h->Q, h->ldq, h->theta, h->d.N, h->stream));
+	h->launches++;
+	return PQP_OK;
+}
+
 static int ensure_batched_operands(pqp_handle *h)
 {
 	if (h->QpT) return PQP_OK;
@@ -528,9 +561,10 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 	const float *Md = (want_status && h->have_fp_model) ? h->Md : NULL;
 	h->ev_valid = 0;
 
-	const int batched = B > 1 && iters > 0 && !strict && pqp_batched_simt_supported(N);
+	const int umma = use_umma_batched(h);
+	const int batched = B > 1 && iters > 0 && !strict && (umma || pqp_batched_simt_supported(N));
 	if (batched) {
-		int rc = ensure_batched_operands(h);
+		int rc = umma ? ensure_umma_tiles(h) : ensure_batched_operands(h);
 		if (rc) return rc;
 		if (Y0) {
 			CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
@@ -539,11 +573,19 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			h->launches++;
 		}
 		CK(cudaEventRecord(h->ev0, h->stream));
-		CK(pqp_launch_batched_simt_split(h->QpT, h->QnT, h->Kpad, h->Ipad, N, B, h->Fd, h->Y, iters, h->stream));
+		if (umma) {
+			int cluster = 4;
+			if (getenv("PQP_UMMA_CLUSTER")) cluster = atoi(getenv("PQP_UMMA_CLUSTER"));
+			if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = 1;
+			CK(pqp_launch_batched_umma(h->umma_tiles, N, B, h->Fd, h->Y, iters, cluster, h->stream));
+			h->last_kernel = "batched_umma";
+		} else {
+			CK(pqp_launch_batched_simt_split(h->QpT, h->QnT, h->Kpad, h->Ipad, N, B, h->Fd, h->Y, iters, h->stream));
+			h->last_kernel = "batched_simt";
+		}
 		CK(cudaEventRecord(h->ev1, h->stream));
 		h->ev_valid = 1;
 		h->launches++;
-		h->last_kernel = "batched_simt";
 		if (want_status) {
 			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, Md, h->Kp, h->o.erc, h->o.eac, B, iters, h->stream));
 			h->launches++;
@@ -671,6 +713,51 @@ int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B,
 	if ((rc = recover_on_device(h, h->Y, h->d.N, NULL, B, U))) return rc;
 	CK(cudaStreamSynchronize(h->stream));
 	return PQP_OK;
+}
+
+/* ---- matrixMultiply (PQP_CPU.c:84-147) on the device ---------------------------------------- */
+int pqp_matmul(float *out, const float *A, int tA, const float *B, int tB, int a, int b, int c, int engine, int device)
+{
+	if (!out || !A || !B || a <= 0 || b <= 0 || c <= 0) return PQP_ERR_INVALID;
+	if (engine != PQP_MM_STRICT && engine != PQP_MM_SIMT && engine != PQP_MM_TENSOR) return PQP_ERR_INVALID;
+	if (pqp_device_count() == 0) return PQP_ERR_NO_DEVICE;
+	if (device >= 0) CK(cudaSetDevice(device));
+	float *dA = NULL, *dB = NULL, *dC = NULL, *dT = NULL;
+	int rc = PQP_OK;
+	cudaStream_t s = 0;
+	if ((rc = dalloc(&dA, (size_t)a * b)) || (rc = dalloc(&dB, (size_t)b * c)) || (rc = dalloc(&dC, (size_t)a * c)) ||
+	    (rc = dalloc(&dT, (size_t)(a > c ? a : c) * b)))
+		goto done;
+	{
+		cudaError_t e = cudaMemcpy(dA, A, (size_t)a * b * sizeof(float), cudaMemcpyDefault);
+		if (e == cudaSuccess) e = cudaMemcpy(dB, B, (size_t)b * c * sizeof(float), cudaMemcpyDefault);
+		/* normalise to A [a x b] row-major (K-major) */
+		const float *Ak = dA;
+		if (e == cudaSuccess && tA) { /* stored [b x a] */
+			e = pqp_launch_transpose(dT, b, dA, a, b, a, s);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(dA, dT, (size_t)a * b * sizeof(float), cudaMemcpyDeviceToDevice, s);
+		}
+		/* and B as Bt [c x b] (K-major) */
+		if (e == cudaSuccess && !tB) { /* stored [b x c] */
+			e = pqp_launch_transpose(dT, b, dB, c, b, c, s);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(dB, dT, (size_t)b * c * sizeof(float), cudaMemcpyDeviceToDevice, s);
+		}
+		if (e == cudaSuccess) {
+			if (engine == PQP_MM_STRICT) e = pqp_launch_matmul_strict(dC, c, Ak, b, dB, b, 1, a, b, c, s);
+			else if (engine == PQP_MM_SIMT) e = pqp_launch_matmul_simt(dC, c, Ak, b, dB, b, 1, a, b, c, s);
+			else e = pqp_launch_gemm_umma(dC, c, Ak, b, dB, b, a, b, c, s);
+		}
+		if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+		if (e == cudaSuccess) e = cudaMemcpy(out, dC, (size_t)a * c * sizeof(float), cudaMemcpyDefault);
+		if (e != cudaSuccess) {
+			snprintf(g_cuda_err, sizeof g_cuda_err, "pqp_matmul -> %s", cudaGetErrorString(e));
+			cudaGetLastError();
+			rc = PQP_ERR_CUDA;
+		}
+	}
+done:
+	cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dT);
+	return rc;
 }
 
 /* ---- introspection ---------------------------------------------------------------------------- */

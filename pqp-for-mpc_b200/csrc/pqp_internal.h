@@ -24,6 +24,9 @@ cudaError_t pqp_launch_matmul_strict(float *C, int ldc, const float *A, int lda,
 /* fp32 SIMT tiled GEMM (FAST mode without tensor cores; also the cross-check for the tcgen05 path) */
 cudaError_t pqp_launch_matmul_simt(float *C, int ldc, const float *A, int lda, const float *B, int ldb, int transB,
 				   int a, int b, int c, cudaStream_t s);
+/* tcgen05 3xTF32 GEMM (pqp_gemm_umma.cu): C[a x c] = A[a x b] * Bt[c x b]', both operands K-major */
+cudaError_t pqp_launch_gemm_umma(float *C, int ldc, const float *A, int lda, const float *Bt, int ldb, int a, int b, int c,
+				 cudaStream_t s);
 /* theta_i = max(sum_j max(0,-Q_ij), floor); strict: thread per row, j ascending */
 cudaError_t pqp_launch_theta(float *theta, const float *Q, int ldq, int N, float floor_, int strict, cudaStream_t s);
 /* out[c x r] (ldo) = in[r x c] (ldi) transposed */
@@ -88,6 +91,12 @@ cudaError_t pqp_launch_build_split_t(float *QpT, float *QnT, int Kpad, int Ipad,
 cudaError_t pqp_launch_batched_simt_split(const float *QpT, const float *QnT, int Kpad, int Ipad, int N, int B,
 					  const float *Fd, float *Y, int iters, cudaStream_t s);
 int pqp_batched_simt_supported(int N);
+/* tcgen05 3xTF32 version (pqp_batched_umma.cu): pre-split, pre-tiled A operand + the loop */
+int pqp_batched_umma_supported(int N);
+size_t pqp_batched_umma_tiles_bytes(int N);
+cudaError_t pqp_launch_build_umma_tiles(void *tiles, const float *Q, int ldq, const float *theta, int N, cudaStream_t s);
+cudaError_t pqp_launch_batched_umma(const void *tiles, int N, int B, const float *Fd, float *Y, int iters, int cluster,
+				    cudaStream_t s);
 #define PQP_BATCH_KPAD 16
 #define PQP_BATCH_IPAD 128
 
