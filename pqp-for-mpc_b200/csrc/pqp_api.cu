@@ -52,10 +52,12 @@ struct pqp_handle {
 	int fp_B; /* problems whose Fp is cached from the last solve */
 	/* single-problem loop state */
 	float *ybuf0, *ybuf1, *partials;
+	void *pk0, *pk1; /* {value, epoch} packet vectors of the flag-in-data y exchange */
 	unsigned *barrier;
 	int *result_buf;
 	int gemv_grid, gemv_resident;
 	int tma_ok, tma_stages, tma_resident, tma_yc, tma_pinned;
+	int small_ok, small_wpr, small_cpt, small_grid;
 	int l2_window_set;
 	long long launches;
 	const char *last_kernel;
@@ -197,12 +199,22 @@ static int finish_setup(pqp_handle *h)
 		h->launches += 1;
 	}
 	if ((rc = dalloc(&h->ybuf0, ldq)) || (rc = dalloc(&h->ybuf1, ldq))) return rc;
+	{
+		double *a0 = NULL, *a1 = NULL;
+		if ((rc = dalloc(&a0, ldq)) || (rc = dalloc(&a1, ldq))) return rc;
+		h->pk0 = a0;
+		h->pk1 = a1;
+	}
 	if ((rc = dalloc(&h->barrier, 4)) || (rc = dalloc(&h->result_buf, 4))) return rc;
 
 	/* persistent-kernel geometry: one CTA per SM, but never fewer than 4 rows per CTA */
 	int grid = h->num_sms;
 	if (grid > (N + 3) / 4) grid = (N + 3) / 4;
 	if (grid < 1) grid = 1;
+	if (getenv("PQP_GEMV_GRID")) {
+		int v = atoi(getenv("PQP_GEMV_GRID"));
+		if (v >= 1 && v <= h->num_sms && v <= N) grid = v;
+	}
 	h->gemv_grid = grid;
 	if ((rc = dalloc(&h->partials, (size_t)2 * grid * 8))) return rc;
 	/* rows of each slab that fit in shared memory next to y and the partial sums */
@@ -225,6 +237,18 @@ static int finish_setup(pqp_handle *h)
 	/* the LDG kernel only parks rows when the whole slab fits; partial residency belongs to the TMA kernel */
 	if (res < rows_max && !env) res = 0;
 	h->gemv_resident = res;
+
+	/* register-resident kernel for small N */
+	h->small_ok = 0;
+	if (h->gemv_grid > 0 && !(getenv("PQP_GEMV_SMALL") && atoi(getenv("PQP_GEMV_SMALL")) == 0)) {
+		/* as FEW CTAs as the 16-rows-per-CTA layout allows: the y exchange costs ~1 us with 32-64 participants and
+		 * ~3.4 us with 148 (measured, tools/gemv_sweep.py N=1024), and the arithmetic is negligible either way */
+		int sg = (N + 15) / 16;
+		if (sg > h->num_sms) sg = h->num_sms;
+		if (getenv("PQP_GEMV_GRID")) sg = h->gemv_grid;
+		h->small_grid = sg;
+		h->small_ok = pqp_gemv_small_plan(N, ldq, sg, &h->small_wpr, &h->small_cpt);
+	}
 
 	/* TMA-staged kernel: ring depth / residency / L2-pinned rows */
 	h->tma_ok = 0;
@@ -425,7 +449,7 @@ void pqp_destroy(pqp_handle *h)
 	}
 	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
 			 h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
-			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf };
+			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf, h->pk0, h->pk1 };
 	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
 		if (ptrs[i]) cudaFree(ptrs[i]);
 	if (h->ev0) cudaEventDestroy(h->ev0);
@@ -497,9 +521,22 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 	}
 
 	if (h->gemv_grid <= 0) return PQP_ERR_UNSUPPORTED;
+	if (iters > 0 && h->small_ok) {
+		h->last_kernel = "gemv_small_registers";
+		a.grid = h->small_grid;
+		CK(pqp_launch_gemv_small(&a, h->small_wpr, h->small_cpt, h->pk0, h->pk1, h->stream));
+		h->launches++;
+		*y_res = h->ybuf1;
+		return PQP_OK;
+	}
 	if (iters > 0 && h->tma_ok) {
 		h->last_kernel = h->tma_resident >= (N + h->gemv_grid - 1) / h->gemv_grid + 1 ? "gemv_tma_resident" : "gemv_tma_stream";
-		CK(pqp_launch_gemv_tma(&a, h->tma_stages, h->tma_resident, h->tma_pinned, h->tma_yc, h->stream));
+		const int ll = !(getenv("PQP_GEMV_LL") && atoi(getenv("PQP_GEMV_LL")) == 0);
+		CK(pqp_launch_gemv_tma(&a, h->tma_stages, h->tma_resident, h->tma_pinned, h->tma_yc, ll ? h->pk0 : NULL, ll ? h->pk1 : NULL,
+				       h->stream));
+		h->launches++;
+		*y_res = ll ? h->ybuf1 : ((iters & 1) ? h->ybuf1 : h->ybuf0);
+		return PQP_OK;
 	} else {
 		h->last_kernel = h->gemv_resident > 0 ? "gemv_persistent_resident" : "gemv_persistent_stream";
 		CK(pqp_launch_gemv_persistent(&a, h->stream));

@@ -111,6 +111,40 @@ __device__ __forceinline__ void grid_barrier_consumers(unsigned *counter, unsign
 	consumer_sync();
 }
 
+/*
+ * Flag-in-data exchange of y ("LL" protocol): every dual travels as an 8-byte packet {value, epoch} written with
+ * one 64-bit store and read with polling loads; a packet is valid for pass p when its epoch equals p.  This fuses
+ * the grid barrier and the y reload into a single L2 round trip per iteration.  Ping-pong safety: a CTA writes
+ * epoch p+2 into buffer p&1 only after it has read ALL of epoch p+1, which exists only once every CTA has finished
+ * reading epoch p (each CTA writes its rows after a CTA-wide sync that follows its reads).
+ */
+__device__ __forceinline__ void st_packet(uint2 *dst, float v, uint32_t epoch)
+{
+	asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ float ld_packet(const uint2 *src, uint32_t epoch)
+{
+	uint32_t v, e;
+	for (;;) {
+		asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
+		if (e == epoch) break;
+		__nanosleep(20);
+	}
+	return __uint_as_float(v);
+}
+/* four consecutive packets -> float4 */
+__device__ __forceinline__ float4 ld_packet4(const uint2 *src, uint32_t epoch)
+{
+	uint32_t a0, e0, a1, e1, a2, e2, a3, e3;
+	for (;;) {
+		asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(e0), "=r"(a1), "=r"(e1) : "l"(src) : "memory");
+		asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a2), "=r"(e2), "=r"(a3), "=r"(e3) : "l"(src + 2) : "memory");
+		if (e0 == epoch && e1 == epoch && e2 == epoch && e3 == epoch) break;
+		__nanosleep(20);
+	}
+	return make_float4(__uint_as_float(a0), __uint_as_float(a1), __uint_as_float(a2), __uint_as_float(a3));
+}
+
 __device__ __forceinline__ void acc4t(float &num, float &den, const float4 q, const float4 y)
 {
 	den = fmaf(fmaxf(q.x, 0.0f), y.x, den);
@@ -129,6 +163,7 @@ struct TmaGeom {
 	int pinned;     /* P streamed rows per slab fetched evict_last */
 	int rows_max;
 	int pol_keep, pol_stream; /* 0 normal, 1 evict_first, 2 evict_last, 3 evict_unchanged */
+	uint2 *pk0, *pk1;         /* packet vectors [ldq] (epochs pre-set to 0xFFFFFFFF), NULL = counter barrier + plain y */
 };
 
 /*
@@ -213,14 +248,34 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 		const float *y_in = (p & 1) ? a.ybuf1 : a.ybuf0;
 		float *y_out = (p & 1) ? a.ybuf0 : a.ybuf1;
 		const bool is_last = (p == passes - 1);
+		const bool ll = g.pk0 != nullptr;
+		const uint2 *pk_in = (p & 1) ? g.pk1 : g.pk0;
+		uint2 *pk_out = (p & 1) ? g.pk0 : g.pk1;
 
 		float4 yv[YC];
+		float y_mine = 0.0f;
+		if (ll && p > 0) {
+			/* columns beyond N carry no packets: the padding of Q is zero, so any finite value works */
 #pragma unroll
-		for (int u = 0; u < YC; u++) {
-			const int c = tid + u * CONSUMERS;
-			yv[u] = (c < n4) ? __ldcg(reinterpret_cast<const float4 *>(y_in) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+			for (int u = 0; u < YC; u++) {
+				const int c = tid + u * CONSUMERS;
+				yv[u] = (c * 4 + 3 < N) ? ld_packet4(pk_in + 4 * c, (uint32_t)p) : make_float4(0.f, 0.f, 0.f, 0.f);
+				if (c * 4 + 3 >= N && c * 4 < N) {
+					float t[4] = { 0.f, 0.f, 0.f, 0.f };
+					for (int e = 0; e < 4; e++)
+						if (c * 4 + e < N) t[e] = ld_packet(pk_in + 4 * c + e, (uint32_t)p);
+					yv[u] = make_float4(t[0], t[1], t[2], t[3]);
+				}
+			}
+			if (tid < nrows) y_mine = ld_packet(pk_in + r0 + tid, (uint32_t)p);
+		} else {
+#pragma unroll
+			for (int u = 0; u < YC; u++) {
+				const int c = tid + u * CONSUMERS;
+				yv[u] = (c < n4) ? __ldcg(reinterpret_cast<const float4 *>(y_in) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+			if (tid < nrows) y_mine = __ldcg(y_in + r0 + tid);
 		}
-		const float y_mine = (tid < nrows) ? __ldcg(y_in + r0 + tid) : 0.0f;
 
 		for (int t = 0; t < nrows; t++) {
 			const float4 *src;
@@ -268,7 +323,13 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 			}
 			num = fmaf(th_r, y_mine, num) + fmaxf(-fd_r, 0.0f);
 			den = fmaf(th_r, y_mine, den) + fmaxf(fd_r, 0.0f);
-			if (!is_last) y_out[r0 + tid] = __fdiv_rn(num, den) * y_mine;
+			if (!is_last) {
+				const float yn = __fdiv_rn(num, den) * y_mine;
+				if (ll) st_packet(pk_out + r0 + tid, yn, (uint32_t)(p + 1));
+				else y_out[r0 + tid] = yn;
+			} else if (ll) {
+				a.ybuf1[r0 + tid] = y_mine; /* the answer, as a plain vector */
+			}
 			if (is_last) {
 				const float gq = den - num;
 				e_min = gq;
@@ -302,7 +363,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 			}
 		}
 
-		grid_barrier_consumers(a.barrier, bar_target, G);
+		if (!ll || is_last) grid_barrier_consumers(a.barrier, bar_target, G);
+		else consumer_sync(); /* part[] and the row constants are reused by the next pass */
 
 		if (is_last && blockIdx.x == 0 && warp == 0) {
 			float v_min = INFINITY, v_gap = 0.0f, v_jd = 0.0f, v_kkt = 0.0f;
@@ -327,7 +389,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 				o.Jd = v_jd + (a.Md ? 0.5f * a.Md[0] : 0.0f);
 				o.kkt = v_kkt;
 				*a.status = o;
-				*a.result_buf = p & 1;
+				*a.result_buf = ll ? 1 : (p & 1);
 			}
 		}
 	}
@@ -376,7 +438,8 @@ int pqp_gemv_tma_plan(int N, int ldq, int grid, size_t smem_budget, int *stages,
 	return 1;
 }
 
-cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident, int pinned, int yc, cudaStream_t s)
+cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident, int pinned, int yc, void *pk0, void *pk1,
+				cudaStream_t s)
 {
 	TmaGeom g;
 	g.stages = stages;
@@ -385,6 +448,13 @@ cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident
 	g.rows_max = (a->N + a->grid - 1) / a->grid + 1;
 	g.pol_keep = 2;
 	g.pol_stream = 1;
+	g.pk0 = reinterpret_cast<uint2 *>(pk0);
+	g.pk1 = reinterpret_cast<uint2 *>(pk1);
+	if (g.pk0) {
+		cudaError_t e0 = cudaMemsetAsync(pk0, 0xFF, (size_t)a->ldq * sizeof(uint2), s);
+		if (e0 == cudaSuccess) e0 = cudaMemsetAsync(pk1, 0xFF, (size_t)a->ldq * sizeof(uint2), s);
+		if (e0 != cudaSuccess) return e0;
+	}
 	if (getenv("PQP_POL_KEEP")) g.pol_keep = atoi(getenv("PQP_POL_KEEP"));
 	if (getenv("PQP_POL_STREAM")) g.pol_stream = atoi(getenv("PQP_POL_STREAM"));
 	const size_t smem = tma_smem_bytes(a->ldq, g);

@@ -76,7 +76,13 @@ cudaError_t pqp_gemv_smem_bytes(int N, int ldq, int grid, int resident_rows, siz
 cudaError_t pqp_launch_gemv_persistent(const pqp_gemv_args *a, cudaStream_t s);
 /* TMA-staged variant (pqp_gemv_tma.cu), fixed-count solves */
 int pqp_gemv_tma_plan(int N, int ldq, int grid, size_t smem_budget, int *stages, int *resident, int *yc);
-cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident, int pinned, int yc, cudaStream_t s);
+/* pk0/pk1: packet vectors [ldq x 8 B] for the flag-in-data y exchange, or NULL for the counter barrier; the
+ * result is left in ybuf1 when packets are used, in ybuf[iters&1] otherwise */
+cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident, int pinned, int yc, void *pk0, void *pk1,
+				cudaStream_t s);
+/* register-resident variant for small N (pqp_gemv_small.cu); result left in ybuf1 */
+int pqp_gemv_small_plan(int N, int ldq, int grid, int *wpr, int *cpt);
+cudaError_t pqp_launch_gemv_small(const pqp_gemv_args *a, int wpr, int cpt, void *pk0, void *pk1, cudaStream_t s);
 /* strict: one launch per iteration, thread i owns row i and walks k ascending over QT */
 cudaError_t pqp_launch_gemv_strict_step(const pqp_gemv_args *a, const float *y_in, float *y_out, cudaStream_t s);
 /* evaluation of the status quantities for one y (any mode) */
