@@ -43,7 +43,8 @@ struct pqp_handle {
 	float *Mp1, *Mp2, *Mp3, *Mp4, *Mp5, *Mp6;
 	float Mp0;
 	float *QpT, *QnT; /* batched operands, built on first batched solve */
-	void *umma_tiles; /* pre-split, pre-tiled tf32 hi/lo operand of the tcgen05 batched kernel */
+	void *umma_tiles; /* pre-split, pre-tiled tf32 hi/lo operand of the tcgen05 3xTF32 batched kernel */
+	void *imma_tiles, *imma_rowc; /* digit planes + row constants of the tcgen05 int8 (error-free) batched kernel */
 	int Kpad, Ipad;
 	/* per-batch workspace */
 	int cap;
@@ -448,7 +449,7 @@ void pqp_destroy(pqp_handle *h)
 		if (h->l2_window_set) l2_persist_window(h, 0);
 	}
 	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
-			 h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
+			 h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
 			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf, h->pk0, h->pk1 };
 	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
 		if (ptrs[i]) cudaFree(ptrs[i]);
@@ -554,14 +555,35 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 	return PQP_OK;
 }
 
-static int use_umma_batched(const pqp_handle *h)
+/* which batched engine: 0 fp32 SIMT, 1 tcgen05 int8 digit planes (error-free accumulation; the default), 2 tcgen05 3xTF32 */
+enum { BATCH_SIMT = 0, BATCH_IMMA = 1, BATCH_UMMA = 2 };
+static int batched_engine(const pqp_handle *h)
 {
-	/* opt-in (use_tensor_cores >= 2 or PQP_BATCHED_UMMA=1): the tensor core's truncating accumulation leaves the
-	 * 3xTF32 loop ~5-100x above the fp32 noise floor after 1000 updates, so the parity-clean fp32
-	 * SIMT kernel stays the default batched path */
-	const char *e = getenv("PQP_BATCHED_UMMA");
-	if (e) return atoi(e) != 0 && pqp_batched_umma_supported(h->d.N);
-	return h->o.use_tensor_cores >= 2 && pqp_batched_umma_supported(h->d.N);
+	/*
+	 * use_tensor_cores: 0 -> SIMT.  1 (default) -> the int8 kernel: exact integer accumulation in TMEM, accuracy of the fp32
+	 * oracle.  2 -> the 3xTF32 kernel: its fp32 accumulator truncates on every step, which leaves the loop
+	 * 5-100x above the fp32 noise floor after 1000 updates, so it is opt-in only.  PQP_BATCHED=simt|imma|umma overrides.
+	 */
+	const char *e = getenv("PQP_BATCHED");
+	int want = h->o.use_tensor_cores <= 0 ? BATCH_SIMT : (h->o.use_tensor_cores >= 2 ? BATCH_UMMA : BATCH_IMMA);
+	if (e) want = !strcmp(e, "simt") ? BATCH_SIMT : (!strcmp(e, "umma") ? BATCH_UMMA : (!strcmp(e, "imma") ? BATCH_IMMA : want));
+	if (getenv("PQP_BATCHED_UMMA")) want = atoi(getenv("PQP_BATCHED_UMMA")) ? BATCH_UMMA : BATCH_SIMT; /* older knob */
+	if (want == BATCH_IMMA && !pqp_batched_imma_supported(h->d.N)) want = BATCH_SIMT;
+	if (want == BATCH_UMMA && !pqp_batched_umma_supported(h->d.N)) want = BATCH_SIMT;
+	return want;
+}
+
+static int ensure_imma_tiles(pqp_handle *h)
+{
+	if (h->imma_tiles) return PQP_OK;
+	unsigned char *t = NULL, *r = NULL;
+	int rc;
+	if ((rc = dalloc(&t, pqp_batched_imma_tiles_bytes(h->d.N))) || (rc = dalloc(&r, pqp_batched_imma_rowc_bytes(h->d.N)))) return rc;
+	h->imma_tiles = t;
+	h->imma_rowc = r;
+	CK(pqp_launch_build_imma_tiles(h->imma_tiles, h->imma_rowc, h->Q, h->ldq, h->theta, h->d.N, h->stream));
+	h->launches++;
+	return PQP_OK;
 }
 
 static int ensure_umma_tiles(pqp_handle *h)
@@ -598,10 +620,10 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 	const float *Md = (want_status && h->have_fp_model) ? h->Md : NULL;
 	h->ev_valid = 0;
 
-	const int umma = use_umma_batched(h);
-	const int batched = B > 1 && iters > 0 && !strict && (umma || pqp_batched_simt_supported(N));
+	const int engine = batched_engine(h);
+	const int batched = B > 1 && iters > 0 && !strict && (engine != BATCH_SIMT || pqp_batched_simt_supported(N));
 	if (batched) {
-		int rc = umma ? ensure_umma_tiles(h) : ensure_batched_operands(h);
+		int rc = engine == BATCH_IMMA ? ensure_imma_tiles(h) : (engine == BATCH_UMMA ? ensure_umma_tiles(h) : ensure_batched_operands(h));
 		if (rc) return rc;
 		if (Y0) {
 			CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
@@ -610,7 +632,16 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			h->launches++;
 		}
 		CK(cudaEventRecord(h->ev0, h->stream));
-		if (umma) {
+		if (engine == BATCH_IMMA) {
+			/* problems per CTA: 32 spreads a small batch over more SMs, 64 halves the operand stream per problem */
+			int nb = B >= 64 * h->num_sms ? 64 : 32;
+			if (getenv("PQP_IMMA_NB")) nb = atoi(getenv("PQP_IMMA_NB")) == 64 ? 64 : 32;
+			int cluster = 1;
+			if (getenv("PQP_IMMA_CLUSTER")) cluster = atoi(getenv("PQP_IMMA_CLUSTER"));
+			if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) cluster = 1;
+			CK(pqp_launch_batched_imma(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, nb, cluster, h->smem_optin, h->stream));
+			h->last_kernel = "batched_imma";
+		} else if (engine == BATCH_UMMA) {
 			int cluster = 4;
 			if (getenv("PQP_UMMA_CLUSTER")) cluster = atoi(getenv("PQP_UMMA_CLUSTER"));
 			if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = 1;

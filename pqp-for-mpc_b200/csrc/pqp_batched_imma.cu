@@ -1,0 +1,538 @@
+/*
+ * pqp_batched_imma.cu -- B problems sharing one Hessian on the 5th-gen tensor cores (sm_100a), with
+ * ERROR-FREE accumulation: tcgen05.mma.kind::i8 over byte slices of the operands, int32 accumulators in TMEM.
+ *
+ * The PQP update for many MPC states at once (PQP_CPU.c:603-618 + 590-596 applied to B right-hand sides)
+ *      NUM = (Q^- + theta) Y + F^-,   DEN = (Q^+ + theta) Y + F^+,   Y <- NUM/DEN o Y,      Y in R^{N x B}
+ * is two N x N x B contractions per iteration (4*N^2*B flop).
+ *
+ * Why integers.  The fp32 accumulator of tcgen05.mma.kind::tf32 truncates on every accumulating step (measured:
+ * ~2.8e-8 relative per MMA, always downwards for the non-negative sums of this algorithm; tools/tc_bias_probe.py).
+ * Over the 120 steps of an N=480 row that is a coherent -3e-6 bias on both sums, which the fixed-point iteration
+ * amplifies well past the 1e-5 parity tolerance.  Integer tensor-core accumulation is exact, so the operands are
+ * cut into byte slices (Ozaki-style splitting) instead:
+ *   off-diagonal Q^+ / Q^- row i :  a_ik = rint(q_ik * 2^(24-e_i))  < 2^24,  a = A0*2^16 + A1*2^8 + A2   (u8 digits; x-independent, built once)
+ *   y of problem b               :  y_k  = rint(y_k  * 2^(22-f_b)) <= 2^22,  y = Y0*2^16 + Y1*2^8 + Y2   (signed s8 digits, round to nearest,
+ *                                   so the dropped cross terms are zero-mean), 2^f_b > max_k y_k, re-derived every iteration
+ *   w0 = A0*Y0,  w1 = A0*Y1 + A1*Y0,  w2 = A0*Y2 + A1*Y1 + A2*Y0      exact in int32 (|w| < 2^26 for N <= 512)
+ *   sum_k q_ik y_k = (w0*2^16 + w1*2^8 + w2) * 2^(e_i-8) * 2^(f_b-22)  up to the 2^-24-level roundings of the fixed-point conversions
+ * The diagonal term (Q^+-_ii + theta_i)*y_i (the largest single term, PQP_CPU.c:527,536) and F^+- are added in fp32 in the
+ * epilogue, the division is IEEE, and the master copy of y stays in fp32 registers: only the tensor-core operand is quantised.
+ * Accuracy measured against the float64 twin of the oracle is that of the fp32 oracle itself (tools/ozaki_emulate.py).
+ *
+ * It is also the cheaper contraction: 6 slice products at the int8 rate (4x tf32) = 1.5 tf32-equivalents instead of 3 (3xTF32),
+ * 3 bytes per operand element instead of 8.
+ *
+ * Mapping (one CTA = NB problems for the WHOLE solve; no grid barrier, no host round trip, no HBM traffic in the loop):
+ *   M = 128 rows of Q (an "M tile"), K = columns of Q (32 per MMA), N = problems x digit planes.
+ *   A operand  = pre-sliced, pre-tiled Q^- / Q^+ digit planes (3 x 4 KB per (matrix, M tile, K step); 1.5 MB at N=480, L2
+ *                resident), streamed through a shared-memory ring by 1-D bulk async copies (UBLKCP), multicast to the CTAs
+ *                of a cluster.
+ *   B operand  = the CTA's Y digit planes [Y0 | Y1 | Y2], MN-major in shared memory for the whole solve (so an epilogue thread,
+ *                which owns one row k and 16 problems, writes its 16 digits with ONE 128-bit store per plane).
+ *   D          = one "unit" (matrix, M tile) = 3*NB int32 columns [w0 | w1 | w2], double buffered in TMEM:
+ *                  MMA(A0, [Y0|Y1|Y2]) -> [w0 w1 w2];  MMA(A1, [Y0|Y1]) -> += [w1 w2];  MMA(A2, [Y0]) -> += [w2]
+ *                so the tensor pipe works on unit u+1 while the epilogue warps drain unit u.
+ *   warp 0     producer (bulk copies + mbarriers), warp 1 MMA issuer (single thread) + TMEM allocator,
+ *   warps 2..  epilogue (4 lane quarters x NB/16 problem groups): tcgen05.ld, int -> fp32, +diag, +F, divide, update the fp32
+ *              master y in registers, per-problem max (redux + shared atomics), requantise, store the digit planes.
+ */
+#include "pqp_internal.h"
+#include "pqp_umma.cuh"
+
+#include <stdlib.h>
+#include <string.h>
+
+#define BI_SLICE 4096u            /* one 128 x 32 u8 tile */
+#define BI_CHUNK (3u * BI_SLICE)  /* three digit planes of one (matrix, M tile, K step) */
+#define BI_A_LBO 2048u            /* K-major A: byte stride between 16-element k groups */
+#define BI_A_SBO 128u             /*            byte stride between 8-row groups */
+#define BI_B_LBO 128u             /* MN-major B: byte stride between 8-k groups (16 problems x 8 k = 128 B core matrix) */
+#define BI_YBITS 22
+#define BI_MAX_MT 4
+
+namespace {
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank()
+{
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(umma::smem_addr(dst)),
+		     "l"(src), "r"(bytes), "r"(umma::smem_addr(bar))
+		     : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_mcast(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint16_t mask)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+			     umma::smem_addr(dst)),
+		     "l"(src), "r"(bytes), "r"(umma::smem_addr(bar)), "h"(mask)
+		     : "memory");
+}
+__device__ __forceinline__ void mma_commit_mcast(uint64_t *bar, uint16_t mask)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+			     umma::smem_addr(bar)),
+		     "h"(mask)
+		     : "memory");
+}
+/* D[tmem] (+)= A[smem, u8, K-major] * B[smem, s8, MN-major]; int32 accumulate (exact) */
+__device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n\t"
+		".reg .pred p;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+		"}" ::"r"(d_tmem),
+		"l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+		: "memory");
+}
+/* instruction descriptor: kind::i8, D = s32, A = u8 K-major, B = s8 MN-major */
+__host__ __device__ constexpr uint32_t idesc_i8(int M, int N)
+{
+	return (2u << 4)                      /* c_format = S32 */
+	       | (0u << 7)                    /* a_format = unsigned 8 bit */
+	       | (1u << 10)                   /* b_format = signed 8 bit */
+	       | (0u << 15)                   /* A K-major */
+	       | (1u << 16)                   /* B MN-major */
+	       | ((uint32_t)(N >> 3) << 17)   /* n_dim */
+	       | ((uint32_t)(M >> 4) << 24);  /* m_dim */
+}
+__device__ __forceinline__ void tmem_ld16_i32(uint32_t taddr, int *v)
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+		     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+		       "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+		     : "r"(taddr)
+		     : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+/* power-of-two scales of a problem whose largest dual has biased exponent field ex (pmax < 2^(ex-126)):
+ * quantise with 2^(22-f), f = ex-126;  undo with 2^(f-22).  ex clamped so both stay normal floats. */
+__device__ __forceinline__ void problem_scales(uint32_t pmax_bits, float &sc, float &isc)
+{
+	uint32_t ex = pmax_bits >> 23;
+	ex = ex < 22u ? 22u : (ex > 254u ? 254u : ex);
+	sc = __uint_as_float((275u - ex) << 23);  /* 2^(148-ex) */
+	isc = __uint_as_float((ex - 21u) << 23);  /* 2^(ex-148) */
+}
+
+} /* namespace */
+
+struct BiParams {
+	const unsigned char *Atiles; /* [MT][2 (neg,pos)][NKS][3 planes][4096 B] */
+	const float4 *rowc;          /* [MT*128] {dn, dp, rsn, rsp}: diagonal terms and row scales (2^(e-8)) */
+	const float *Fd;             /* [B x N] */
+	float *Y;                    /* [B x N] in: y0, out: y_K */
+	int N, B, iters;
+	int MT, NKS;                 /* M tiles of 128 rows, K steps of 32 */
+	int stages;                  /* ring depth */
+	uint32_t b_sbo;              /* B operand: byte stride between 16-problem groups = Kpad*16 */
+	int dbg;                     /* experiment switches (PQP_IMMA_DBG): 1 skip A1/A2 MMAs, 2 skip all MMAs, 4 skip epilogue math */
+};
+
+/*
+ * shared memory: ring [stages][BI_CHUNK] | B planes [3][NB/16][Kpad/8][8][16 B] | smax[2][NB] | iscale[2][NB] | barriers
+ */
+template <int NB>
+__global__ void __launch_bounds__(64 + 8 * NB, 1) batched_imma_kernel(const BiParams p)
+{
+	constexpr int EW = NB / 4;           /* epilogue warps: 4 lane quarters x NB/16 problem groups */
+	constexpr int ETHREADS = 32 * EW;
+	constexpr uint32_t UNIT_COLS = 3 * NB;
+	constexpr uint32_t TMEM_COLS = (2 * UNIT_COLS <= 128) ? 128u : ((2 * UNIT_COLS <= 256) ? 256u : 512u);
+
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+	const uint32_t CS = cluster_nctarank(), crank = cluster_ctarank();
+	const uint16_t cmask = (uint16_t)((1u << CS) - 1u);
+
+	const int N = p.N, MT = p.MT, NKS = p.NKS;
+	const int Kpad = NKS * 32;
+	unsigned char *ring = smem_raw;
+	unsigned char *Bpl = ring + (size_t)p.stages * BI_CHUNK;
+	const uint32_t plane_bytes = (uint32_t)(NB / 16) * p.b_sbo;
+	uint32_t *smax = reinterpret_cast<uint32_t *>(Bpl + 3u * plane_bytes);
+	float *iscale = reinterpret_cast<float *>(smax + 2 * NB);
+	uint64_t *full = reinterpret_cast<uint64_t *>(iscale + 2 * NB);
+	uint64_t *empty = full + p.stages;
+	uint64_t *tmem_full = empty + p.stages;   /* [2] */
+	uint64_t *tmem_empty = tmem_full + 2;     /* [2] */
+	uint64_t *b_ready = tmem_empty + 2;
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_ready + 1);
+
+	const int units_per_iter = 2 * MT;
+	const int chunks_per_iter = units_per_iter * NKS;
+	const long long total_chunks = (long long)chunks_per_iter * p.iters;
+	const int b0 = blockIdx.x * NB;
+
+	if (tid == 0) {
+		for (int s = 0; s < p.stages; s++) {
+			umma::mbar_init(&full[s], 1);
+			umma::mbar_init(&empty[s], CS);
+		}
+		for (int i = 0; i < 2; i++) {
+			umma::mbar_init(&tmem_full[i], 1);
+			umma::mbar_init(&tmem_empty[i], ETHREADS);
+		}
+		umma::mbar_init(b_ready, ETHREADS);
+		umma::mbar_fence_init();
+	}
+	if (tid < 2 * NB) smax[tid] = 0u;
+	if (warp == 1) umma::tmem_alloc(tmem_slot, TMEM_COLS);
+	umma::tc_fence_before();
+	__syncthreads();
+	if (CS > 1) cluster_sync_all(); /* every CTA's barriers exist before anyone multicasts into them */
+	umma::tc_fence_after();
+	const uint32_t tmem = *tmem_slot;
+
+	if (warp == 0) {
+		/* ================= producer: A chunks through the ring ================= */
+		if (lane == 0) {
+			int s = 0;
+			uint32_t ph = 0;
+			int within = 0;
+			for (long long c = 0; c < total_chunks; c++) {
+				umma::mbar_wait(&empty[s], ph ^ 1u);
+				umma::mbar_arrive_expect_tx(&full[s], BI_CHUNK);
+				const unsigned char *src = p.Atiles + (size_t)within * BI_CHUNK;
+				if (CS == 1)
+					bulk_g2s_plain(ring + (size_t)s * BI_CHUNK, src, BI_CHUNK, &full[s]);
+				else if ((uint32_t)(c % CS) == crank)
+					bulk_g2s_mcast(ring + (size_t)s * BI_CHUNK, src, BI_CHUNK, &full[s], cmask);
+				if (++within == chunks_per_iter) within = 0;
+				if (++s == p.stages) { s = 0; ph ^= 1u; }
+			}
+		}
+	} else if (warp == 1) {
+		/* ================= MMA issuer ================= */
+		if (lane == 0) {
+			const uint32_t id3 = idesc_i8(128, 3 * NB), id2 = idesc_i8(128, 2 * NB), id1 = idesc_i8(128, NB);
+			const uint32_t b_addr = umma::smem_addr(Bpl);
+			int s = 0;
+			uint32_t ph = 0;
+			long long unit = 0;
+			for (int it = 0; it < p.iters; it++) {
+				umma::mbar_wait(b_ready, (uint32_t)(it & 1)); /* digit planes of this iteration are in place */
+				umma::tc_fence_after();
+				for (int u = 0; u < units_per_iter; u++, unit++) {
+					const int buf = u & 1;
+					umma::mbar_wait(&tmem_empty[buf], (uint32_t)(((unit >> 1) & 1) ^ 1)); /* epilogue drained this buffer */
+					umma::tc_fence_after();
+					const uint32_t d = tmem + (uint32_t)buf * UNIT_COLS;
+					for (int ks = 0; ks < NKS; ks++) {
+						umma::mbar_wait(&full[s], ph);
+						umma::tc_fence_after();
+						const uint32_t a0 = umma::smem_addr(ring + (size_t)s * BI_CHUNK);
+						const uint64_t db = umma::smem_desc(b_addr + (uint32_t)ks * 4u * BI_B_LBO, BI_B_LBO, p.b_sbo);
+						if (!(p.dbg & 2)) {
+							mma_i8(d, umma::smem_desc(a0, BI_A_LBO, BI_A_SBO), db, id3, ks ? 1u : 0u);
+							if (!(p.dbg & 1)) {
+								mma_i8(d + NB, umma::smem_desc(a0 + BI_SLICE, BI_A_LBO, BI_A_SBO), db, id2, 1u);
+								mma_i8(d + 2 * NB, umma::smem_desc(a0 + 2 * BI_SLICE, BI_A_LBO, BI_A_SBO), db, id1, 1u);
+							}
+						}
+						if (CS == 1) umma::mma_commit(&empty[s]);
+						else mma_commit_mcast(&empty[s], cmask); /* the stage is free once EVERY CTA of the cluster has read it */
+						if (++s == p.stages) { s = 0; ph ^= 1u; }
+					}
+					umma::mma_commit(&tmem_full[buf]);
+				}
+			}
+		}
+	} else {
+		/* ================= epilogue warps ================= */
+		const int et = tid - 64;
+		const int ew = warp - 2;
+		const int q = warp % 4;    /* TMEM lane quarter this warp may touch */
+		const int cg = ew / 4;     /* which 16 of the NB problems */
+		const int pb = cg * 16;
+		const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
+		const int r = 32 * q + lane; /* row within an M tile */
+
+		float y[BI_MAX_MT][16];    /* fp32 master copy of this thread's duals: rows mt*128+r, problems pb..pb+15 */
+		float4 rc[BI_MAX_MT];
+
+		/* writes the digit planes of this thread's rows from y[][]; needs scale sc[j] per problem */
+		auto store_planes = [&](const float(&sc)[16]) {
+#pragma unroll
+			for (int mt = 0; mt < BI_MAX_MT; mt++) {
+				const int i = mt * 128 + r;
+				if (mt < MT && i < Kpad) {
+					uint32_t w0[4] = { 0, 0, 0, 0 }, w1[4] = { 0, 0, 0, 0 }, w2[4] = { 0, 0, 0, 0 };
+#pragma unroll
+					for (int j = 0; j < 16; j++) {
+						const int b = __float2int_rn(y[mt][j] * sc[j]);
+						const int d2 = (int)(signed char)b;
+						const int b1 = (b - d2) >> 8;
+						const int d1 = (int)(signed char)b1;
+						const int d0 = (b1 - d1) >> 8;
+						w0[j >> 2] |= ((uint32_t)d0 & 255u) << (8 * (j & 3));
+						w1[j >> 2] |= ((uint32_t)d1 & 255u) << (8 * (j & 3));
+						w2[j >> 2] |= ((uint32_t)d2 & 255u) << (8 * (j & 3));
+					}
+					unsigned char *dst = Bpl + (uint32_t)cg * p.b_sbo + (uint32_t)(i >> 3) * BI_B_LBO + (uint32_t)(i & 7) * 16u;
+					*reinterpret_cast<uint4 *>(dst) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+					*reinterpret_cast<uint4 *>(dst + plane_bytes) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+					*reinterpret_cast<uint4 *>(dst + 2u * plane_bytes) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+				}
+			}
+		};
+		/* per-problem max over this thread's rows -> shared atomics (non-negative floats order like their bit patterns) */
+		auto publish_max = [&](uint32_t *dstmax) {
+#pragma unroll
+			for (int j = 0; j < 16; j++) {
+				float m = 0.0f;
+#pragma unroll
+				for (int mt = 0; mt < BI_MAX_MT; mt++)
+					if (mt < MT) m = fmaxf(m, y[mt][j]);
+				const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+				if (lane == j) atomicMax(dstmax + pb + j, wm);
+			}
+		};
+		/* after everyone published: derive the scales, remember the inverse for the accumulator conversion, store planes */
+		auto requantise = [&](int parity) {
+			named_bar_sync(1, ETHREADS);
+			float sc[16];
+#pragma unroll
+			for (int j = 0; j < 16; j++) {
+				float isc;
+				problem_scales(smax[parity * NB + pb + j], sc[j], isc);
+				if (q == 0 && lane == j) iscale[parity * NB + pb + j] = isc;
+			}
+			store_planes(sc);
+			umma::fence_proxy_async(); /* the new planes must be visible to the tensor core's reads */
+		};
+
+		/* iteration 0: load y0 and the row constants */
+#pragma unroll
+		for (int mt = 0; mt < BI_MAX_MT; mt++) {
+			const int i = mt * 128 + r;
+			rc[mt] = make_float4(0.f, 0.f, 0.f, 0.f);
+			if (mt < MT) rc[mt] = __ldg(p.rowc + i);
+#pragma unroll
+			for (int j = 0; j < 16; j++) {
+				float v = 0.0f;
+				if (mt < MT && i < N && b0 + pb + j < p.B) v = p.Y[(size_t)(b0 + pb + j) * N + i];
+				y[mt][j] = v;
+			}
+		}
+		publish_max(smax + NB); /* parity 1 = "planes for iteration 0" (so iteration it publishes into parity it&1) */
+		requantise(1);
+		umma::mbar_arrive(b_ready);
+
+		long long pair = 0; /* (iteration, M tile) counter: completion index of tmem_full[0] and [1] */
+		for (int it = 0; it < p.iters; it++) {
+			const int par_in = (it & 1) ^ 1; /* scales the planes of this iteration were quantised with */
+			const int par_out = it & 1;
+			float isc[16];
+#pragma unroll
+			for (int mt = 0; mt < BI_MAX_MT; mt++) {
+				if (mt < MT) {
+					const int i = mt * 128 + r;
+					float fd[16];
+#pragma unroll
+					for (int j = 0; j < 16; j++) fd[j] = (i < N && b0 + pb + j < p.B) ? __ldg(p.Fd + (size_t)(b0 + pb + j) * N + i) : 1.0f;
+					float sn[16];
+#pragma unroll
+					for (int mat = 0; mat < 2; mat++) {
+						umma::mbar_wait(&tmem_full[mat], (uint32_t)(pair & 1));
+						umma::tc_fence_after();
+						if (mt == 0 && mat == 0) {
+							/* first unit of the iteration: every thread is past the previous requantise -> safe to read the
+							 * inverse scales and to reset the max slots the NEXT requantise will use */
+#pragma unroll
+							for (int j = 0; j < 16; j++) isc[j] = iscale[par_in * NB + pb + j];
+							if (et < NB) smax[par_out * NB + et] = 0u;
+							named_bar_sync(2, ETHREADS);
+						}
+						const uint32_t col = tmem + lane_addr + (uint32_t)mat * UNIT_COLS + (uint32_t)pb;
+						int w0[16], w1[16], w2[16];
+						tmem_ld16_i32(col, w0);
+						tmem_ld16_i32(col + NB, w1);
+						tmem_ld16_i32(col + 2 * NB, w2);
+						tmem_ld_wait();
+						umma::tc_fence_before();
+						umma::mbar_arrive(&tmem_empty[mat]); /* the tensor pipe may start the next unit in this buffer */
+						const float rs = mat == 0 ? rc[mt].z : rc[mt].w;
+						const float dg = mat == 0 ? rc[mt].x : rc[mt].y;
+						if (!(p.dbg & 4)) {
+#pragma unroll
+							for (int j = 0; j < 16; j++) {
+								/* (w0*2^16 + w1*2^8 + w2) * 2^(e-8) * 2^(f-22): two fused roundings, then exact scalings */
+								const float t = fmaf((float)w0[j], 65536.0f, fmaf((float)w1[j], 256.0f, (float)w2[j]));
+								const float S = __fmul_rn(__fmul_rn(t, rs), isc[j]);
+								const float dy = __fmul_rn(dg, y[mt][j]);
+								if (mat == 0) {
+									sn[j] = __fadd_rn(__fadd_rn(S, dy), fmaxf(-fd[j], 0.0f));
+								} else {
+									const float den = __fadd_rn(__fadd_rn(S, dy), fmaxf(fd[j], 0.0f));
+									if (i < N) y[mt][j] = __fmul_rn(__fdiv_rn(sn[j], den), y[mt][j]);
+								}
+							}
+						}
+					}
+					pair++;
+				}
+			}
+			publish_max(smax + par_out * NB);
+			requantise(par_out);
+			umma::mbar_arrive(b_ready);
+		}
+		/* result: the fp32 master copy */
+#pragma unroll
+		for (int mt = 0; mt < BI_MAX_MT; mt++) {
+			const int i = mt * 128 + r;
+			if (mt < MT && i < N) {
+#pragma unroll
+				for (int j = 0; j < 16; j++)
+					if (b0 + pb + j < p.B) p.Y[(size_t)(b0 + pb + j) * N + i] = y[mt][j];
+			}
+		}
+	}
+	umma::tc_fence_before();
+	__syncthreads();
+	if (CS > 1) cluster_sync_all(); /* nobody leaves while a peer may still multicast into / arrive on this CTA */
+	if (warp == 1) umma::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+/*
+ * Builds the digit planes of the off-diagonal Q^- / Q^+ and the per-row constants (x-independent, once per handle).
+ * One warp per (row, matrix): pass 1 finds the row maximum, pass 2 quantises and scatters the bytes into the tiles.
+ */
+__global__ void build_imma_tiles_kernel(unsigned char *__restrict__ tiles, float4 *__restrict__ rowc, const float *__restrict__ Q, int ldq,
+					 const float *__restrict__ theta, int N, int MT, int NKS)
+{
+	const int lane = threadIdx.x % 32;
+	const int gw = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+	const int nw = gridDim.x * blockDim.x / 32;
+	const int rows = MT * 128, Kpad = NKS * 32;
+	for (int i = gw; i < rows; i += nw) {
+		float dg[2] = { 0.f, 0.f }, rs[2] = { 0.f, 0.f };
+		for (int mat = 0; mat < 2; mat++) {
+			const float sgn = mat == 0 ? -1.0f : 1.0f;
+			float m = 0.0f;
+			if (i < N)
+				for (int k = lane; k < N; k += 32)
+					if (k != i) m = fmaxf(m, fmaxf(sgn * Q[(size_t)i * ldq + k], 0.0f));
+			m = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m)));
+			/* m < 2^e with e = ex-126; entries are scaled by 2^(24-e) = 2^(150-ex); the epilogue undoes it with 2^(e-8) (2^16 folded in) */
+			uint32_t ex = __float_as_uint(m) >> 23;
+			float scale = 0.0f;
+			if (m > 0.0f && ex >= 32u && ex <= 254u) { /* rows whose largest entry is below 2^-95 are treated as zero */
+				scale = __uint_as_float((277u - ex) << 23);  /* 2^(150-ex) */
+				rs[mat] = __uint_as_float((ex - 7u) << 23);  /* 2^(ex-134) = 2^(e-8) */
+			}
+			if (i < N) {
+				const float qii = Q[(size_t)i * ldq + i];
+				dg[mat] = __fadd_rn(fmaxf(sgn * qii, 0.0f), theta[i]); /* theta added on the diagonal, PQP_CPU.c:527,536 */
+			}
+			for (int k = lane; k < Kpad; k += 32) {
+				uint32_t a = 0;
+				if (i < N && k < N && k != i) a = __float2uint_rn(fmaxf(sgn * Q[(size_t)i * ldq + k], 0.0f) * scale);
+				const int mt = i / 128, rr = i % 128, ks = k / 32, kk = k % 32;
+				unsigned char *blk = tiles + ((size_t)(mt * 2 + mat) * NKS + ks) * BI_CHUNK;
+				const uint32_t off = (uint32_t)(kk / 16) * BI_A_LBO + (uint32_t)(rr / 8) * BI_A_SBO + (uint32_t)(rr % 8) * 16u + (uint32_t)(kk % 16);
+				blk[off] = (unsigned char)(a >> 16);
+				blk[BI_SLICE + off] = (unsigned char)((a >> 8) & 255u);
+				blk[2 * BI_SLICE + off] = (unsigned char)(a & 255u);
+			}
+		}
+		if (lane == 0) rowc[i] = make_float4(dg[0], dg[1], rs[0], rs[1]);
+	}
+}
+
+int pqp_batched_imma_supported(int N) { return N >= 16 && N <= 128 * BI_MAX_MT; }
+
+size_t pqp_batched_imma_tiles_bytes(int N)
+{
+	const int MT = (N + 127) / 128, NKS = (N + 31) / 32;
+	return (size_t)2 * MT * NKS * BI_CHUNK;
+}
+size_t pqp_batched_imma_rowc_bytes(int N) { return (size_t)((N + 127) / 128) * 128 * sizeof(float4); }
+
+cudaError_t pqp_launch_build_imma_tiles(void *tiles, void *rowc, const float *Q, int ldq, const float *theta, int N, cudaStream_t s)
+{
+	const int MT = (N + 127) / 128, NKS = (N + 31) / 32;
+	build_imma_tiles_kernel<<<148, 256, 0, s>>>(reinterpret_cast<unsigned char *>(tiles), reinterpret_cast<float4 *>(rowc), Q, ldq, theta, N,
+						    MT, NKS);
+	return cudaGetLastError();
+}
+
+template <int NB>
+static cudaError_t launch_imma(const BiParams &p0, int cluster, size_t smem_optin, cudaStream_t s)
+{
+	BiParams p = p0;
+	const int Kpad = p.NKS * 32;
+	const size_t fixed = 3 * (size_t)(NB / 16) * p.b_sbo + 4 * NB * sizeof(uint32_t) + 64 /* barriers besides the ring's */ + 16;
+	(void)Kpad;
+	int stages = (int)((smem_optin - 1024 - fixed) / (BI_CHUNK + 16));
+	if (stages > 16) stages = 16;
+	if (getenv("PQP_IMMA_STAGES")) {
+		const int v = atoi(getenv("PQP_IMMA_STAGES"));
+		if (v >= 2 && v <= stages) stages = v;
+	}
+	if (stages < 2) return cudaErrorInvalidConfiguration;
+	p.stages = stages;
+	const size_t smem = (size_t)stages * BI_CHUNK + fixed + (size_t)stages * 16;
+	cudaError_t e = cudaFuncSetAttribute(batched_imma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return e;
+	if (cluster < 1) cluster = 1;
+	if (cluster > 8) {
+		e = cudaFuncSetAttribute(batched_imma_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+		if (e != cudaSuccess) return e;
+	}
+	int ctas = (p.B + NB - 1) / NB;
+	ctas = (ctas + cluster - 1) / cluster * cluster;
+	cudaLaunchConfig_t cfg;
+	memset(&cfg, 0, sizeof cfg);
+	cfg.gridDim = dim3(ctas);
+	cfg.blockDim = dim3(64 + 8 * NB);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = s;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = cluster;
+	attr[0].val.clusterDim.y = 1;
+	attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, batched_imma_kernel<NB>, p);
+}
+
+cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters, int nb,
+				    int cluster, size_t smem_optin, cudaStream_t s)
+{
+	BiParams p;
+	memset(&p, 0, sizeof p);
+	p.Atiles = reinterpret_cast<const unsigned char *>(tiles);
+	p.rowc = reinterpret_cast<const float4 *>(rowc);
+	p.Fd = Fd;
+	p.Y = Y;
+	p.N = N;
+	p.B = B;
+	p.iters = iters;
+	p.MT = (N + 127) / 128;
+	p.NKS = (N + 31) / 32;
+	p.b_sbo = (uint32_t)(p.NKS * 32) * 16u;
+	p.dbg = getenv("PQP_IMMA_DBG") ? atoi(getenv("PQP_IMMA_DBG")) : 0;
+	if (nb == 64) return launch_imma<64>(p, cluster, smem_optin, s);
+	return launch_imma<32>(p, cluster, smem_optin, s);
+}

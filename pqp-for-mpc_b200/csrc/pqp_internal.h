@@ -103,6 +103,13 @@ size_t pqp_batched_umma_tiles_bytes(int N);
 cudaError_t pqp_launch_build_umma_tiles(void *tiles, const float *Q, int ldq, const float *theta, int N, cudaStream_t s);
 cudaError_t pqp_launch_batched_umma(const void *tiles, int N, int B, const float *Fd, float *Y, int iters, int cluster,
 				    cudaStream_t s);
+/* tcgen05 int8 digit-plane version (pqp_batched_imma.cu): error-free integer accumulation */
+int pqp_batched_imma_supported(int N);
+size_t pqp_batched_imma_tiles_bytes(int N);
+size_t pqp_batched_imma_rowc_bytes(int N);
+cudaError_t pqp_launch_build_imma_tiles(void *tiles, void *rowc, const float *Q, int ldq, const float *theta, int N, cudaStream_t s);
+cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters, int nb,
+				    int cluster, size_t smem_optin, cudaStream_t s);
 #define PQP_BATCH_KPAD 16
 #define PQP_BATCH_IPAD 128
 
