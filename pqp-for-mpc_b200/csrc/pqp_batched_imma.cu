@@ -40,6 +40,7 @@
 #include "pqp_internal.h"
 #include "pqp_umma.cuh"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -50,6 +51,12 @@
 #define BI_B_LBO 128u             /* MN-major B: byte stride between 8-k groups (16 problems x 8 k = 128 B core matrix) */
 #define BI_YBITS 22
 #define BI_MAX_MT 4
+/* wait-time profile slots (experiment aid, PQP_IMMA_DBG=8) */
+enum { PROF_MMA_TOTAL = 0, PROF_MMA_WAIT_BREADY, PROF_MMA_WAIT_TMEM, PROF_MMA_WAIT_FULL, PROF_EPI_TOTAL, PROF_EPI_WAIT_TMEM, PROF_EPI_REQUANT,
+       PROF_PROD_WAIT_EMPTY };
+#define PROF_T(var) const long long var = prof_on ? clock64() : 0
+#define PROF_ADD(slot, t0) \
+	if (prof_on) prof_acc[slot] += clock64() - (t0)
 
 namespace {
 
@@ -102,6 +109,73 @@ __device__ __forceinline__ void mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_
 		"l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
 		: "memory");
 }
+/* one lane of a converged warp (the tensor-core / bulk-copy instructions take uniform operands: issuing them from
+ * warp-uniform code under elect.sync lets ptxas keep the descriptors in uniform registers) */
+__device__ __forceinline__ bool elect_one()
+{
+	uint32_t pred;
+	asm volatile(
+		"{\n\t"
+		".reg .pred p;\n\t"
+		"elect.sync _|p, 0xffffffff;\n\t"
+		"selp.u32 %0, 1, 0, p;\n\t"
+		"}"
+		: "=r"(pred));
+	return pred != 0;
+}
+/* the three MMAs of one K step: planes A0, A1, A2 (4 KB apart) against [Y0|Y1|Y2], [Y0|Y1], [Y0] */
+__device__ __forceinline__ void mma_i8_step(uint32_t d, uint32_t d1, uint32_t d2, uint64_t a_desc, uint64_t b_desc, uint32_t id3, uint32_t id2,
+					    uint32_t id1, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n\t"
+		".reg .pred p, pt;\n\t"
+		".reg .b64 a1, a2;\n\t"
+		"setp.ne.b32 p, %8, 0;\n\t"
+		"setp.eq.b32 pt, 0, 0;\n\t"
+		"add.s64 a1, %3, 256;\n\t"
+		"add.s64 a2, %3, 512;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%0], %3, %4, %5, p;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%1], a1, %4, %6, pt;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%2], a2, %4, %7, pt;\n\t"
+		"}" ::"r"(d),
+		"r"(d1), "r"(d2), "l"(a_desc), "l"(b_desc), "r"(id3), "r"(id2), "r"(id1), "r"(accumulate)
+		: "memory");
+}
+/* three consecutive K steps (a 36 KB ring stage) in one go: 9 MMAs, descriptors derived inside the asm block so the
+ * issuing thread moves its operands to uniform registers once per stage instead of once per K step */
+__device__ __forceinline__ void mma_i8_step3(uint32_t d, uint32_t d1, uint32_t d2, uint64_t a_desc, uint64_t b_desc, uint32_t id3, uint32_t id2,
+					     uint32_t id1, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n\t"
+		".reg .pred p, pt;\n\t"
+		".reg .b64 a01, a02, a10, a11, a12, a20, a21, a22, b1, b2;\n\t"
+		"setp.ne.b32 p, %8, 0;\n\t"
+		"setp.eq.b32 pt, 0, 0;\n\t"
+		"add.s64 a01, %3, 256;\n\t"
+		"add.s64 a02, %3, 512;\n\t"
+		"add.s64 a10, %3, 768;\n\t"
+		"add.s64 a11, %3, 1024;\n\t"
+		"add.s64 a12, %3, 1280;\n\t"
+		"add.s64 a20, %3, 1536;\n\t"
+		"add.s64 a21, %3, 1792;\n\t"
+		"add.s64 a22, %3, 2048;\n\t"
+		"add.s64 b1, %4, 32;\n\t"
+		"add.s64 b2, %4, 64;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%0], %3, %4, %5, p;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%1], a01, %4, %6, pt;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%2], a02, %4, %7, pt;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%0], a10, b1, %5, pt;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%1], a11, b1, %6, pt;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%2], a12, b1, %7, pt;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%0], a20, b2, %5, pt;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%1], a21, b2, %6, pt;\n\t"
+		"tcgen05.mma.cta_group::1.kind::i8 [%2], a22, b2, %7, pt;\n\t"
+		"}" ::"r"(d),
+		"r"(d1), "r"(d2), "l"(a_desc), "l"(b_desc), "r"(id3), "r"(id2), "r"(id1), "r"(accumulate)
+		: "memory");
+}
 /* instruction descriptor: kind::i8, D = s32, A = u8 K-major, B = s8 MN-major */
 __host__ __device__ constexpr uint32_t idesc_i8(int M, int N)
 {
@@ -120,6 +194,18 @@ __device__ __forceinline__ void tmem_ld16_i32(uint32_t taddr, int *v)
 		       "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
 		     : "r"(taddr)
 		     : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_i32(uint32_t taddr, int *v)
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+		     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+		     : "r"(taddr)
+		     : "memory");
+}
+template <int PW> __device__ __forceinline__ void tmem_ld_i32(uint32_t taddr, int *v)
+{
+	if (PW == 16) tmem_ld16_i32(taddr, v);
+	else tmem_ld8_i32(taddr, v);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -142,19 +228,22 @@ struct BiParams {
 	const float *Fd;             /* [B x N] */
 	float *Y;                    /* [B x N] in: y0, out: y_K */
 	int N, B, iters;
-	int MT, NKS;                 /* M tiles of 128 rows, K steps of 32 */
+	int MT, NKS;                 /* M tiles of 128 rows, K steps of 32 (padded to a multiple of ksc) */
+	int ksc;                     /* K steps per ring stage: 3 (36 KB stages) or 1 */
+	int dbuf;                    /* 1: two plane buffers -> new digits are stored speculatively while the MMAs still read the old ones */
 	int stages;                  /* ring depth */
 	uint32_t b_sbo;              /* B operand: byte stride between 16-problem groups = Kpad*16 */
-	int dbg;                     /* experiment switches (PQP_IMMA_DBG): 1 skip A1/A2 MMAs, 2 skip all MMAs, 4 skip epilogue math */
+	int dbg;                     /* experiment switches (PQP_IMMA_DBG): 2 skip all MMAs, 4 skip epilogue math, 8 print wait-time profile */
+	long long *prof;             /* dbg & 8: [8] cycle counters of CTA 0 (see PROF_*) */
 };
 
 /*
- * shared memory: ring [stages][BI_CHUNK] | B planes [3][NB/16][Kpad/8][8][16 B] | smax[2][NB] | iscale[2][NB] | barriers
+ * shared memory: ring [stages][ksc*BI_CHUNK] | B planes [3][NB/16][Kpad/8][8][16 B] | smax[2][NB] | iscale[2][NB] | barriers
  */
-template <int NB>
-__global__ void __launch_bounds__(64 + 8 * NB, 1) batched_imma_kernel(const BiParams p)
+template <int NB, int PW>
+__global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(const BiParams p)
 {
-	constexpr int EW = NB / 4;           /* epilogue warps: 4 lane quarters x NB/16 problem groups */
+	constexpr int EW = 4 * (NB / PW);    /* epilogue warps: 4 lane quarters x NB/PW problem groups of PW problems per thread */
 	constexpr int ETHREADS = 32 * EW;
 	constexpr uint32_t UNIT_COLS = 3 * NB;
 	constexpr uint32_t TMEM_COLS = (2 * UNIT_COLS <= 128) ? 128u : ((2 * UNIT_COLS <= 256) ? 256u : 512u);
@@ -167,9 +256,12 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) batched_imma_kernel(const BiPa
 	const int N = p.N, MT = p.MT, NKS = p.NKS;
 	const int Kpad = NKS * 32;
 	unsigned char *ring = smem_raw;
-	unsigned char *Bpl = ring + (size_t)p.stages * BI_CHUNK;
+	const uint32_t stage_bytes = (uint32_t)p.ksc * BI_CHUNK;
+	unsigned char *Bpl = ring + (size_t)p.stages * stage_bytes;
 	const uint32_t plane_bytes = (uint32_t)(NB / 16) * p.b_sbo;
-	uint32_t *smax = reinterpret_cast<uint32_t *>(Bpl + 3u * plane_bytes);
+	const uint32_t pbuf_bytes = 3u * plane_bytes;                 /* one buffer = the three digit planes */
+	const uint32_t nbuf = p.dbuf ? 2u : 1u;
+	uint32_t *smax = reinterpret_cast<uint32_t *>(Bpl + nbuf * pbuf_bytes);
 	float *iscale = reinterpret_cast<float *>(smax + 2 * NB);
 	uint64_t *full = reinterpret_cast<uint64_t *>(iscale + 2 * NB);
 	uint64_t *empty = full + p.stages;
@@ -179,9 +271,12 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) batched_imma_kernel(const BiPa
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_ready + 1);
 
 	const int units_per_iter = 2 * MT;
-	const int chunks_per_iter = units_per_iter * NKS;
+	const int chunks_per_unit = NKS / p.ksc;
+	const int chunks_per_iter = units_per_iter * chunks_per_unit;
 	const long long total_chunks = (long long)chunks_per_iter * p.iters;
 	const int b0 = blockIdx.x * NB;
+	const bool prof_on = (p.dbg & 8) && p.prof && blockIdx.x == 0;
+	long long prof_acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
 
 	if (tid == 0) {
 		for (int s = 0; s < p.stages; s++) {
@@ -196,6 +291,8 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) batched_imma_kernel(const BiPa
 		umma::mbar_fence_init();
 	}
 	if (tid < 2 * NB) smax[tid] = 0u;
+	for (uint32_t i = tid; i < nbuf * pbuf_bytes / 16u; i += blockDim.x) reinterpret_cast<uint4 *>(Bpl)[i] = make_uint4(0u, 0u, 0u, 0u);
+	umma::fence_proxy_async(); /* K padding of the planes is never rewritten: make the zeros visible to the tensor core's reads */
 	if (warp == 1) umma::tmem_alloc(tmem_slot, TMEM_COLS);
 	umma::tc_fence_before();
 	__syncthreads();
@@ -204,120 +301,159 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) batched_imma_kernel(const BiPa
 	const uint32_t tmem = *tmem_slot;
 
 	if (warp == 0) {
-		/* ================= producer: A chunks through the ring ================= */
-		if (lane == 0) {
-			int s = 0;
-			uint32_t ph = 0;
-			int within = 0;
-			for (long long c = 0; c < total_chunks; c++) {
-				umma::mbar_wait(&empty[s], ph ^ 1u);
-				umma::mbar_arrive_expect_tx(&full[s], BI_CHUNK);
-				const unsigned char *src = p.Atiles + (size_t)within * BI_CHUNK;
+		/* ================= producer: A chunks through the ring (whole warp, one elected lane issues) ================= */
+		int st = 0;
+		uint32_t ph = 0;
+		int within = 0;
+		for (long long c = 0; c < total_chunks; c++) {
+			PROF_T(tw);
+			umma::mbar_wait(&empty[st], ph ^ 1u);
+			PROF_ADD(PROF_PROD_WAIT_EMPTY, tw);
+			if (elect_one()) {
+				umma::mbar_arrive_expect_tx(&full[st], stage_bytes);
+				const unsigned char *src = p.Atiles + (size_t)within * stage_bytes;
 				if (CS == 1)
-					bulk_g2s_plain(ring + (size_t)s * BI_CHUNK, src, BI_CHUNK, &full[s]);
+					bulk_g2s_plain(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st]);
 				else if ((uint32_t)(c % CS) == crank)
-					bulk_g2s_mcast(ring + (size_t)s * BI_CHUNK, src, BI_CHUNK, &full[s], cmask);
-				if (++within == chunks_per_iter) within = 0;
-				if (++s == p.stages) { s = 0; ph ^= 1u; }
+					bulk_g2s_mcast(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st], cmask);
 			}
+			__syncwarp();
+			if (++within == chunks_per_iter) within = 0;
+			if (++st == p.stages) { st = 0; ph ^= 1u; }
 		}
+		if (prof_on && lane == 0) p.prof[PROF_PROD_WAIT_EMPTY] = prof_acc[PROF_PROD_WAIT_EMPTY];
 	} else if (warp == 1) {
-		/* ================= MMA issuer ================= */
-		if (lane == 0) {
-			const uint32_t id3 = idesc_i8(128, 3 * NB), id2 = idesc_i8(128, 2 * NB), id1 = idesc_i8(128, NB);
-			const uint32_t b_addr = umma::smem_addr(Bpl);
-			int s = 0;
-			uint32_t ph = 0;
-			long long unit = 0;
-			for (int it = 0; it < p.iters; it++) {
-				umma::mbar_wait(b_ready, (uint32_t)(it & 1)); /* digit planes of this iteration are in place */
+		/* ================= MMA issuer (whole warp in uniform control flow, one elected lane issues) ================= */
+		const uint32_t id3 = idesc_i8(128, 3 * NB), id2 = idesc_i8(128, 2 * NB), id1 = idesc_i8(128, NB);
+		const uint64_t a_desc0 = umma::smem_desc(umma::smem_addr(ring), BI_A_LBO, BI_A_SBO);
+		const uint64_t b_desc0 = umma::smem_desc(umma::smem_addr(Bpl), BI_B_LBO, p.b_sbo);
+		int st = 0;
+		uint32_t ph = 0;
+		long long unit = 0;
+		PROF_T(tm0);
+		for (int it = 0; it < p.iters; it++) {
+			PROF_T(tb);
+			umma::mbar_wait(b_ready, (uint32_t)(it & 1)); /* digit planes of this iteration are in place */
+			PROF_ADD(PROF_MMA_WAIT_BREADY, tb);
+			umma::tc_fence_after();
+			for (int u = 0; u < units_per_iter; u++, unit++) {
+				const int buf = u & 1;
+				PROF_T(te);
+				umma::mbar_wait(&tmem_empty[buf], (uint32_t)(((unit >> 1) & 1) ^ 1)); /* epilogue drained this buffer */
+				PROF_ADD(PROF_MMA_WAIT_TMEM, te);
 				umma::tc_fence_after();
-				for (int u = 0; u < units_per_iter; u++, unit++) {
-					const int buf = u & 1;
-					umma::mbar_wait(&tmem_empty[buf], (uint32_t)(((unit >> 1) & 1) ^ 1)); /* epilogue drained this buffer */
+				const uint32_t d = tmem + (uint32_t)buf * UNIT_COLS;
+				for (int ch = 0; ch < chunks_per_unit; ch++) {
+					PROF_T(tf);
+					umma::mbar_wait(&full[st], ph);
+					PROF_ADD(PROF_MMA_WAIT_FULL, tf);
 					umma::tc_fence_after();
-					const uint32_t d = tmem + (uint32_t)buf * UNIT_COLS;
-					for (int ks = 0; ks < NKS; ks++) {
-						umma::mbar_wait(&full[s], ph);
-						umma::tc_fence_after();
-						const uint32_t a0 = umma::smem_addr(ring + (size_t)s * BI_CHUNK);
-						const uint64_t db = umma::smem_desc(b_addr + (uint32_t)ks * 4u * BI_B_LBO, BI_B_LBO, p.b_sbo);
+					if (elect_one()) {
+						/* only the 14-bit start-address field of the descriptors moves: +768 per 12 KB of ring, +32 per K step */
+						const uint64_t da = a_desc0 + (uint64_t)((uint32_t)st * (stage_bytes >> 4));
+						const uint64_t db = b_desc0 + (uint64_t)((uint32_t)(ch * p.ksc) * (4u * BI_B_LBO >> 4) + ((p.dbuf && (it & 1)) ? (pbuf_bytes >> 4) : 0u));
 						if (!(p.dbg & 2)) {
-							mma_i8(d, umma::smem_desc(a0, BI_A_LBO, BI_A_SBO), db, id3, ks ? 1u : 0u);
-							if (!(p.dbg & 1)) {
-								mma_i8(d + NB, umma::smem_desc(a0 + BI_SLICE, BI_A_LBO, BI_A_SBO), db, id2, 1u);
-								mma_i8(d + 2 * NB, umma::smem_desc(a0 + 2 * BI_SLICE, BI_A_LBO, BI_A_SBO), db, id1, 1u);
-							}
+							if (p.ksc == 3) mma_i8_step3(d, d + NB, d + 2 * NB, da, db, id3, id2, id1, ch ? 1u : 0u);
+							else mma_i8_step(d, d + NB, d + 2 * NB, da, db, id3, id2, id1, ch ? 1u : 0u);
 						}
-						if (CS == 1) umma::mma_commit(&empty[s]);
-						else mma_commit_mcast(&empty[s], cmask); /* the stage is free once EVERY CTA of the cluster has read it */
-						if (++s == p.stages) { s = 0; ph ^= 1u; }
+						if (CS == 1) umma::mma_commit(&empty[st]);
+						else mma_commit_mcast(&empty[st], cmask); /* the stage is free once EVERY CTA of the cluster has read it */
 					}
-					umma::mma_commit(&tmem_full[buf]);
+					__syncwarp();
+					if (++st == p.stages) { st = 0; ph ^= 1u; }
 				}
+				if (elect_one()) umma::mma_commit(&tmem_full[buf]);
+				__syncwarp();
 			}
 		}
+		PROF_ADD(PROF_MMA_TOTAL, tm0);
+		if (prof_on && lane == 0)
+			for (int i = PROF_MMA_TOTAL; i <= PROF_MMA_WAIT_FULL; i++) p.prof[i] = prof_acc[i];
 	} else {
 		/* ================= epilogue warps ================= */
 		const int et = tid - 64;
 		const int ew = warp - 2;
 		const int q = warp % 4;    /* TMEM lane quarter this warp may touch */
-		const int cg = ew / 4;     /* which 16 of the NB problems */
-		const int pb = cg * 16;
+		const int cg = ew / 4;     /* which PW of the NB problems */
+		const int pb = cg * PW;
 		const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
 		const int r = 32 * q + lane; /* row within an M tile */
 
-		float y[BI_MAX_MT][16];    /* fp32 master copy of this thread's duals: rows mt*128+r, problems pb..pb+15 */
+		float y[BI_MAX_MT][PW];    /* fp32 master copy of this thread's duals: rows mt*128+r, problems pb..pb+PW-1 */
 		float4 rc[BI_MAX_MT];
 
-		/* writes the digit planes of this thread's rows from y[][]; needs scale sc[j] per problem */
-		auto store_planes = [&](const float(&sc)[16]) {
+		/* digits of one M tile of this thread's rows (y[mt][0..15] scaled by sc[j]) -> plane buffer `buf` */
+		auto store_tile = [&](int mt, const float(&yv)[PW], const float(&sc)[PW], uint32_t buf) {
+			const int i = mt * 128 + r;
+			if (i < Kpad) {
+				uint32_t w0[4] = { 0, 0, 0, 0 }, w1[4] = { 0, 0, 0, 0 }, w2[4] = { 0, 0, 0, 0 };
 #pragma unroll
-			for (int mt = 0; mt < BI_MAX_MT; mt++) {
-				const int i = mt * 128 + r;
-				if (mt < MT && i < Kpad) {
-					uint32_t w0[4] = { 0, 0, 0, 0 }, w1[4] = { 0, 0, 0, 0 }, w2[4] = { 0, 0, 0, 0 };
-#pragma unroll
-					for (int j = 0; j < 16; j++) {
-						const int b = __float2int_rn(y[mt][j] * sc[j]);
-						const int d2 = (int)(signed char)b;
-						const int b1 = (b - d2) >> 8;
-						const int d1 = (int)(signed char)b1;
-						const int d0 = (b1 - d1) >> 8;
-						w0[j >> 2] |= ((uint32_t)d0 & 255u) << (8 * (j & 3));
-						w1[j >> 2] |= ((uint32_t)d1 & 255u) << (8 * (j & 3));
-						w2[j >> 2] |= ((uint32_t)d2 & 255u) << (8 * (j & 3));
-					}
-					unsigned char *dst = Bpl + (uint32_t)cg * p.b_sbo + (uint32_t)(i >> 3) * BI_B_LBO + (uint32_t)(i & 7) * 16u;
+				for (int j = 0; j < PW; j++) {
+					const int b = __float2int_rn(yv[j] * sc[j]);
+					const int d2 = (int)(signed char)b;
+					const int b1 = (b - d2) >> 8;
+					const int d1 = (int)(signed char)b1;
+					const int d0 = (b1 - d1) >> 8;
+					w0[j >> 2] |= ((uint32_t)d0 & 255u) << (8 * (j & 3));
+					w1[j >> 2] |= ((uint32_t)d1 & 255u) << (8 * (j & 3));
+					w2[j >> 2] |= ((uint32_t)d2 & 255u) << (8 * (j & 3));
+				}
+				unsigned char *dst = Bpl + buf * pbuf_bytes + (uint32_t)(pb >> 4) * p.b_sbo + (uint32_t)(i >> 3) * BI_B_LBO + (uint32_t)(i & 7) * 16u +
+						     (uint32_t)(pb & 15);
+				if (PW == 16) {
 					*reinterpret_cast<uint4 *>(dst) = make_uint4(w0[0], w0[1], w0[2], w0[3]);
 					*reinterpret_cast<uint4 *>(dst + plane_bytes) = make_uint4(w1[0], w1[1], w1[2], w1[3]);
 					*reinterpret_cast<uint4 *>(dst + 2u * plane_bytes) = make_uint4(w2[0], w2[1], w2[2], w2[3]);
+				} else {
+					*reinterpret_cast<uint2 *>(dst) = make_uint2(w0[0], w0[1]);
+					*reinterpret_cast<uint2 *>(dst + plane_bytes) = make_uint2(w1[0], w1[1]);
+					*reinterpret_cast<uint2 *>(dst + 2u * plane_bytes) = make_uint2(w2[0], w2[1]);
 				}
 			}
 		};
-		/* per-problem max over this thread's rows -> shared atomics (non-negative floats order like their bit patterns) */
-		auto publish_max = [&](uint32_t *dstmax) {
+		auto store_planes = [&](const float(&sc)[PW], uint32_t buf) {
 #pragma unroll
-			for (int j = 0; j < 16; j++) {
-				float m = 0.0f;
+			for (int mt = 0; mt < BI_MAX_MT; mt++)
+				if (mt < MT) store_tile(mt, y[mt], sc, buf);
+		};
+		/* per-problem max of one M tile's new duals -> shared atomics (non-negative floats order like their bit patterns;
+		 * NaN patterns order above everything, which is what lets a NaN poison its whole problem below) */
+		auto publish_tile_max = [&](const float(&yv)[PW], uint32_t *dstmax) {
 #pragma unroll
-				for (int mt = 0; mt < BI_MAX_MT; mt++)
-					if (mt < MT) m = fmaxf(m, y[mt][j]);
-				const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+			for (int j = 0; j < PW; j++) {
+				const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(yv[j]) & 0x7fffffffu);
 				if (lane == j) atomicMax(dstmax + pb + j, wm);
 			}
 		};
-		/* after everyone published: derive the scales, remember the inverse for the accumulator conversion, store planes */
-		auto requantise = [&](int parity) {
+		/*
+		 * After everyone published: the exact per-problem maxima are known.  Derive the scales, remember the inverses for the
+		 * accumulator conversion of the next iteration, and make sure plane buffer `buf` holds digits quantised with exactly these
+		 * scales: `have_ex` < 0 means nothing has been stored yet; otherwise the tiles were already stored speculatively with the
+		 * scales of exponent field pred_bits>>23 and only need redoing where the exponent moved.
+		 * A problem whose maximum is not finite is set to NaN as a whole: the reference's dense sums do exactly that one
+		 * iteration later (0*NaN = NaN in every row), whereas the quantiser would silently drop the NaN.
+		 */
+		auto requantise = [&](int parity, uint32_t buf, bool speculated, int par_pred) {
 			named_bar_sync(1, ETHREADS);
-			float sc[16];
+			float sc[PW];
+			bool redo = !speculated;
 #pragma unroll
-			for (int j = 0; j < 16; j++) {
+			for (int j = 0; j < PW; j++) {
+				const uint32_t mx = smax[parity * NB + pb + j];
 				float isc;
-				problem_scales(smax[parity * NB + pb + j], sc[j], isc);
+				problem_scales(mx, sc[j], isc);
 				if (q == 0 && lane == j) iscale[parity * NB + pb + j] = isc;
+				if ((mx >> 23) >= 255u) {
+#pragma unroll
+					for (int mt = 0; mt < BI_MAX_MT; mt++) y[mt][j] = __uint_as_float(0x7fc00000u);
+				}
+				if (speculated) {
+					float scp, iscp;
+					problem_scales(smax[par_pred * NB + pb + j], scp, iscp);
+					redo = redo || (scp != sc[j]);
+				}
 			}
-			store_planes(sc);
+			if (redo) store_planes(sc, buf);
 			umma::fence_proxy_async(); /* the new planes must be visible to the tensor core's reads */
 		};
 
@@ -328,46 +464,51 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) batched_imma_kernel(const BiPa
 			rc[mt] = make_float4(0.f, 0.f, 0.f, 0.f);
 			if (mt < MT) rc[mt] = __ldg(p.rowc + i);
 #pragma unroll
-			for (int j = 0; j < 16; j++) {
+			for (int j = 0; j < PW; j++) {
 				float v = 0.0f;
 				if (mt < MT && i < N && b0 + pb + j < p.B) v = p.Y[(size_t)(b0 + pb + j) * N + i];
 				y[mt][j] = v;
 			}
 		}
-		publish_max(smax + NB); /* parity 1 = "planes for iteration 0" (so iteration it publishes into parity it&1) */
-		requantise(1);
+#pragma unroll
+		for (int mt = 0; mt < BI_MAX_MT; mt++)
+			if (mt < MT) publish_tile_max(y[mt], smax + NB); /* parity 1 = "planes for iteration 0" (iteration it publishes into parity it&1) */
+		requantise(1, 0u, false, 0);
 		umma::mbar_arrive(b_ready);
 
 		long long pair = 0; /* (iteration, M tile) counter: completion index of tmem_full[0] and [1] */
+		PROF_T(te0);
 		for (int it = 0; it < p.iters; it++) {
 			const int par_in = (it & 1) ^ 1; /* scales the planes of this iteration were quantised with */
 			const int par_out = it & 1;
-			float isc[16];
+			float isc[PW];
 #pragma unroll
 			for (int mt = 0; mt < BI_MAX_MT; mt++) {
 				if (mt < MT) {
 					const int i = mt * 128 + r;
-					float fd[16];
+					float fd[PW];
 #pragma unroll
-					for (int j = 0; j < 16; j++) fd[j] = (i < N && b0 + pb + j < p.B) ? __ldg(p.Fd + (size_t)(b0 + pb + j) * N + i) : 1.0f;
-					float sn[16];
+					for (int j = 0; j < PW; j++) fd[j] = (i < N && b0 + pb + j < p.B) ? __ldg(p.Fd + (size_t)(b0 + pb + j) * N + i) : 1.0f;
+					float sn[PW];
 #pragma unroll
 					for (int mat = 0; mat < 2; mat++) {
+						PROF_T(tw);
 						umma::mbar_wait(&tmem_full[mat], (uint32_t)(pair & 1));
+						PROF_ADD(PROF_EPI_WAIT_TMEM, tw);
 						umma::tc_fence_after();
 						if (mt == 0 && mat == 0) {
 							/* first unit of the iteration: every thread is past the previous requantise -> safe to read the
 							 * inverse scales and to reset the max slots the NEXT requantise will use */
 #pragma unroll
-							for (int j = 0; j < 16; j++) isc[j] = iscale[par_in * NB + pb + j];
+							for (int j = 0; j < PW; j++) isc[j] = iscale[par_in * NB + pb + j];
 							if (et < NB) smax[par_out * NB + et] = 0u;
 							named_bar_sync(2, ETHREADS);
 						}
 						const uint32_t col = tmem + lane_addr + (uint32_t)mat * UNIT_COLS + (uint32_t)pb;
-						int w0[16], w1[16], w2[16];
-						tmem_ld16_i32(col, w0);
-						tmem_ld16_i32(col + NB, w1);
-						tmem_ld16_i32(col + 2 * NB, w2);
+						int w0[PW], w1[PW], w2[PW];
+						tmem_ld_i32<PW>(col, w0);
+						tmem_ld_i32<PW>(col + NB, w1);
+						tmem_ld_i32<PW>(col + 2 * NB, w2);
 						tmem_ld_wait();
 						umma::tc_fence_before();
 						umma::mbar_arrive(&tmem_empty[mat]); /* the tensor pipe may start the next unit in this buffer */
@@ -375,7 +516,7 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) batched_imma_kernel(const BiPa
 						const float dg = mat == 0 ? rc[mt].x : rc[mt].y;
 						if (!(p.dbg & 4)) {
 #pragma unroll
-							for (int j = 0; j < 16; j++) {
+							for (int j = 0; j < PW; j++) {
 								/* (w0*2^16 + w1*2^8 + w2) * 2^(e-8) * 2^(f-22): two fused roundings, then exact scalings */
 								const float t = fmaf((float)w0[j], 65536.0f, fmaf((float)w1[j], 256.0f, (float)w2[j]));
 								const float S = __fmul_rn(__fmul_rn(t, rs), isc[j]);
@@ -390,19 +531,35 @@ __global__ void __launch_bounds__(64 + 8 * NB, 1) batched_imma_kernel(const BiPa
 						}
 					}
 					pair++;
+					/* this tile's new duals are final: publish their maxima, and (two plane buffers) store their digits right away
+					 * with the scales of the previous maxima -- almost always the exponent the exact maxima will confirm */
+					publish_tile_max(y[mt], smax + par_out * NB);
+					if (p.dbuf) {
+						float scp[PW];
+#pragma unroll
+						for (int j = 0; j < PW; j++) {
+							float iscp;
+							problem_scales(smax[par_in * NB + pb + j], scp[j], iscp);
+						}
+						store_tile(mt, y[mt], scp, (uint32_t)(par_out ^ 1) & 1u);
+					}
 				}
 			}
-			publish_max(smax + par_out * NB);
-			requantise(par_out);
+			PROF_T(tq);
+			requantise(par_out, p.dbuf ? ((uint32_t)(it + 1) & 1u) : 0u, p.dbuf != 0, par_in);
 			umma::mbar_arrive(b_ready);
+			PROF_ADD(PROF_EPI_REQUANT, tq);
 		}
+		PROF_ADD(PROF_EPI_TOTAL, te0);
+		if (prof_on && et == 0)
+			for (int i = PROF_EPI_TOTAL; i <= PROF_EPI_REQUANT; i++) p.prof[i] = prof_acc[i];
 		/* result: the fp32 master copy */
 #pragma unroll
 		for (int mt = 0; mt < BI_MAX_MT; mt++) {
 			const int i = mt * 128 + r;
 			if (mt < MT && i < N) {
 #pragma unroll
-				for (int j = 0; j < 16; j++)
+				for (int j = 0; j < PW; j++)
 					if (b0 + pb + j < p.B) p.Y[(size_t)(b0 + pb + j) * N + i] = y[mt][j];
 			}
 		}
@@ -461,29 +618,47 @@ __global__ void build_imma_tiles_kernel(unsigned char *__restrict__ tiles, float
 
 int pqp_batched_imma_supported(int N) { return N >= 16 && N <= 128 * BI_MAX_MT; }
 
+/* K steps per ring stage and the padded K-step count: stages of 3 K steps (36 KB) keep the issuing thread off the
+ * critical path; tiny problems keep single-step stages */
+static void imma_geometry(int N, int *MT, int *NKS, int *ksc)
+{
+	int nks = (N + 31) / 32;
+	int k = nks >= 3 ? 3 : 1;
+	if (getenv("PQP_IMMA_KSC") && atoi(getenv("PQP_IMMA_KSC")) == 1) k = 1;
+	*ksc = k;
+	*NKS = (nks + k - 1) / k * k;
+	*MT = (N + 127) / 128;
+}
+
 size_t pqp_batched_imma_tiles_bytes(int N)
 {
-	const int MT = (N + 127) / 128, NKS = (N + 31) / 32;
+	int MT, NKS, ksc;
+	imma_geometry(N, &MT, &NKS, &ksc);
 	return (size_t)2 * MT * NKS * BI_CHUNK;
 }
 size_t pqp_batched_imma_rowc_bytes(int N) { return (size_t)((N + 127) / 128) * 128 * sizeof(float4); }
 
 cudaError_t pqp_launch_build_imma_tiles(void *tiles, void *rowc, const float *Q, int ldq, const float *theta, int N, cudaStream_t s)
 {
-	const int MT = (N + 127) / 128, NKS = (N + 31) / 32;
+	int MT, NKS, ksc;
+	imma_geometry(N, &MT, &NKS, &ksc);
 	build_imma_tiles_kernel<<<148, 256, 0, s>>>(reinterpret_cast<unsigned char *>(tiles), reinterpret_cast<float4 *>(rowc), Q, ldq, theta, N,
 						    MT, NKS);
 	return cudaGetLastError();
 }
 
-template <int NB>
+template <int NB, int PW>
 static cudaError_t launch_imma(const BiParams &p0, int cluster, size_t smem_optin, cudaStream_t s)
 {
 	BiParams p = p0;
-	const int Kpad = p.NKS * 32;
-	const size_t fixed = 3 * (size_t)(NB / 16) * p.b_sbo + 4 * NB * sizeof(uint32_t) + 64 /* barriers besides the ring's */ + 16;
-	(void)Kpad;
-	int stages = (int)((smem_optin - 1024 - fixed) / (BI_CHUNK + 16));
+	const size_t pbuf = 3 * (size_t)(NB / 16) * p.b_sbo;
+	const size_t stage_bytes = (size_t)p.ksc * BI_CHUNK;
+	const size_t misc = 4 * NB * sizeof(uint32_t) + 64 /* barriers besides the ring's */ + 16;
+	/* two plane buffers when at least three ring stages still fit beside them */
+	p.dbuf = (2 * pbuf + misc + 3 * (stage_bytes + 16) + 1024 <= smem_optin) ? 1 : 0;
+	if (getenv("PQP_IMMA_DBUF")) p.dbuf = p.dbuf && atoi(getenv("PQP_IMMA_DBUF")) != 0;
+	const size_t fixed = (p.dbuf ? 2 : 1) * pbuf + misc;
+	int stages = (int)((smem_optin - 1024 - fixed) / (stage_bytes + 16));
 	if (stages > 16) stages = 16;
 	if (getenv("PQP_IMMA_STAGES")) {
 		const int v = atoi(getenv("PQP_IMMA_STAGES"));
@@ -491,12 +666,12 @@ static cudaError_t launch_imma(const BiParams &p0, int cluster, size_t smem_opti
 	}
 	if (stages < 2) return cudaErrorInvalidConfiguration;
 	p.stages = stages;
-	const size_t smem = (size_t)stages * BI_CHUNK + fixed + (size_t)stages * 16;
-	cudaError_t e = cudaFuncSetAttribute(batched_imma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	const size_t smem = (size_t)stages * stage_bytes + fixed + (size_t)stages * 16;
+	cudaError_t e = cudaFuncSetAttribute(batched_imma_kernel<NB, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	if (cluster < 1) cluster = 1;
 	if (cluster > 8) {
-		e = cudaFuncSetAttribute(batched_imma_kernel<NB>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+		e = cudaFuncSetAttribute(batched_imma_kernel<NB, PW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 		if (e != cudaSuccess) return e;
 	}
 	int ctas = (p.B + NB - 1) / NB;
@@ -504,7 +679,7 @@ static cudaError_t launch_imma(const BiParams &p0, int cluster, size_t smem_opti
 	cudaLaunchConfig_t cfg;
 	memset(&cfg, 0, sizeof cfg);
 	cfg.gridDim = dim3(ctas);
-	cfg.blockDim = dim3(64 + 8 * NB);
+	cfg.blockDim = dim3(64 + 128 * (NB / PW));
 	cfg.dynamicSmemBytes = smem;
 	cfg.stream = s;
 	cudaLaunchAttribute attr[1];
@@ -514,7 +689,7 @@ static cudaError_t launch_imma(const BiParams &p0, int cluster, size_t smem_opti
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	return cudaLaunchKernelEx(&cfg, batched_imma_kernel<NB>, p);
+	return cudaLaunchKernelEx(&cfg, batched_imma_kernel<NB, PW>, p);
 }
 
 cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters, int nb,
@@ -529,10 +704,30 @@ cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, 
 	p.N = N;
 	p.B = B;
 	p.iters = iters;
-	p.MT = (N + 127) / 128;
-	p.NKS = (N + 31) / 32;
+	imma_geometry(N, &p.MT, &p.NKS, &p.ksc);
 	p.b_sbo = (uint32_t)(p.NKS * 32) * 16u;
 	p.dbg = getenv("PQP_IMMA_DBG") ? atoi(getenv("PQP_IMMA_DBG")) : 0;
-	if (nb == 64) return launch_imma<64>(p, cluster, smem_optin, s);
-	return launch_imma<32>(p, cluster, smem_optin, s);
+	static long long *prof_dev = NULL;
+	if (p.dbg & 8) {
+		if (!prof_dev) cudaMalloc((void **)&prof_dev, 8 * sizeof(long long));
+		cudaMemsetAsync(prof_dev, 0, 8 * sizeof(long long), s);
+		p.prof = prof_dev;
+	}
+	/* PW = problems per epilogue thread: 8 doubles the epilogue warps of the 32-problem tile (16 instead of 8), which is what
+	 * hides the latency of its dependent fp32 chain (division, conversions) behind the tensor pipe */
+	const int pw = getenv("PQP_IMMA_PW") ? atoi(getenv("PQP_IMMA_PW")) : 8;
+	cudaError_t e = nb == 64 ? launch_imma<64, 16>(p, cluster, smem_optin, s)
+				 : (pw == 16 ? launch_imma<32, 16>(p, cluster, smem_optin, s) : launch_imma<32, 8>(p, cluster, smem_optin, s));
+	if ((p.dbg & 8) && e == cudaSuccess) {
+		long long h[8];
+		cudaStreamSynchronize(s);
+		cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost);
+		const double it = (double)iters;
+		fprintf(stderr,
+			"imma profile (CTA 0, cycles per iteration): mma warp total %.0f = wait b_ready %.0f + wait tmem_empty %.0f + wait full(stream) %.0f + issue %.0f | "
+			"epilogue total %.0f = wait tmem_full %.0f + requantise %.0f + drain/math %.0f | producer wait empty %.0f\n",
+			h[0] / it, h[1] / it, h[2] / it, h[3] / it, (h[0] - h[1] - h[2] - h[3]) / it, h[4] / it, h[5] / it, h[6] / it,
+			(h[4] - h[5] - h[6]) / it, h[7] / it);
+	}
+	return e;
 }

@@ -86,6 +86,8 @@ def run(Qd, theta, Fd, K, ybits=22, y_init=1000.0, Y0=None):
         den = ((out[1] + (dp[:, None] * Y).astype(f32)).astype(f32) + Fp_).astype(f32)
         with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
             Y = ((num / den).astype(f32) * Y).astype(f32)
+        # a problem whose largest dual is not finite turns NaN as a whole (what the reference's dense sums do one update later)
+        Y[:, ~np.isfinite(Y).all(axis=0)] = np.nan
     return np.ascontiguousarray(Y.T)
 
 
