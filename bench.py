@@ -51,6 +51,43 @@ def env_int(name, default):
         return default
 
 
+def ncu_traffic(kernel):
+    """dram bytes read+written per launch of `kernel`, from the committed `ncu --set full` summary (profiles/ncu_traffic.json,
+    written by tools/ncu_summary.py); None if that kernel has not been captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except (OSError, ValueError):
+        return None
+
+
+def batched_roofline(kernel, tfl, k_ms, flop_iter, N, B, iters):
+    """Tensor-bound roofline of the batched loop.  achieved = ALGORITHMIC flop (4*N^2*B per update: the two N x N x B
+    contractions of PQP_CPU.c:608-609 in fp32 terms) / the kernel's own time; peak = the measured dense bf16 tensor throughput
+    (MEASURED_PEAKS.json, sustained: the launch runs for tens of ms) -- the only measured tensor figure there is.  The int8
+    kernel spends 6 digit-plane products per algorithmic product on padded 128-row tiles; `executed_int8_tops` is what the
+    tensor pipe actually ran, against the nominal 4500 dense int8 TOP/s of a B200."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1500.0)))
+    src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md ~1.5 PFLOP/s dense bf16)"
+    out = {"bound": "tensor", "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak, "traffic": ncu_traffic(kernel),
+           "peak_source": src, "kernel": kernel, "kernel_ms_per_step": k_ms, "flop_per_iteration": flop_iter,
+           "note": "fp32-equivalent flop 4*N^2*B per update"}
+    if kernel == "batched_imma":
+        mt, nks = (N + 127) // 128, (N + 31) // 32
+        nks = (nks + 2) // 3 * 3 if nks >= 3 else nks
+        ctas = (B + 31) // 32
+        macs = 2 * mt * nks * 128 * (96 + 64 + 32) * 32 * ctas  # per update: (matrix, M tile, K step) x three MMAs of N = 96, 64, 32
+        tops = 2.0 * macs * iters / (k_ms * 1e-3) / 1e12
+        out.update(executed_int8_tops=tops, executed_frac_of_nominal_int8=tops / 4500.0,
+                   note=out["note"] + "; 6 int8 digit-plane products per fp32 product, exact int32 accumulation in TMEM")
+    return out
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -141,27 +178,54 @@ def cpu_updates_for(N, seconds=6.0):
     return max(3, int(max(seconds - setup, 1.0) / per_it))
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_parallel_rate(engine, Qd, Fd, updates, threads):
+    """`threads` independent replicas of the reference loop at once (the reference itself is single-threaded, PQP_CPU.c has no
+    OpenMP/pthreads: the only way it uses more cores is more problems).  ctypes releases the GIL during the C call.
+    Returns (aggregate updates/s, wall seconds)."""
+    from concurrent.futures import ThreadPoolExecutor
+    if threads == 1:
+        return cpu_single_rate(engine, Qd, Fd, updates)
+    ys = [np.full(Fd.size, 1000.0, np.float32) for _ in range(threads)]
+    with ThreadPoolExecutor(threads) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(lambda y: engine.iterate(y, Qd, Fd, updates), ys))
+        dt = time.perf_counter() - t0
+    return threads * updates / dt, dt
+
+
 def run_reference(args, w, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref = PQP_CPU.c compiled where it lay; the
+    oracle port if that library did not travel) on the box's host cores, all of them, one independent problem per thread."""
     if rank != 0:
         return
     engine, kind = cpu_engine()
+    threads = host_threads()
     out = {"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
     if w["kind"] == "single":
         prob, d, Qd, Fd = single_problem_host(w)
+        # memory: every replica builds its own two dense split matrices (8 N^2 bytes), as the reference does per call
+        threads = max(1, min(threads, int(24e9 // (8.0 * w["N"] * w["N"]))))
         upd = cpu_updates_for(w["N"], 4.0)
         for _ in range(args.warmup):
-            cpu_single_rate(engine, Qd, Fd, max(1, upd // 4))
-        rates, t = [], 0.0
+            cpu_parallel_rate(engine, Qd, Fd, max(1, upd // 4), threads)
+        t = 0.0
         for _ in range(args.steps):
-            r, dt = cpu_single_rate(engine, Qd, Fd, upd)
-            rates.append(r)
+            _, dt = cpu_parallel_rate(engine, Qd, Fd, upd, threads)
             t += dt
-        value = upd * args.steps / t
-        sample = f"{upd} PQP updates of the N={w['N']} instance per step (a full step is {args.iters}); includes the reference's per-call split setup"
+        value = threads * upd * args.steps / t
+        sample = (f"{threads} independent replicas of the N={w['N']} instance, {upd} PQP updates each per step (a full step is "
+                  f"{args.iters}); includes the reference's per-call split setup")
         out.update(metric="pqp_iters_per_sec", unit="iterations/s", value=value, ms_per_step=1e3 * t / args.steps,
                    config={"workload": args.workload, "N": w["N"], "M": w["M"], "seed": w["seed"], "iters_per_step": upd,
-                           "l2": "inputs larger than L2" if w["N"] >= 8192 else "n/a (CPU)"})
+                           "replicas": threads, "l2": "inputs larger than L2" if w["N"] >= 8192 else "n/a (CPU)"})
     else:
         from bench_problems import condensed_mpc
         prob, d, X = condensed_mpc(w["seed"], w["pH"], w["nS"], w["nI"], n_states=8)
@@ -171,16 +235,16 @@ def run_reference(args, w, rank, world):
         Qd, Fd, _, _ = o.convert_to_dual(prob["Qp_inv"], prob["Gp"], prob["Kp"], Fp, 0.0)
         upd = 2000
         for _ in range(args.warmup):
-            cpu_single_rate(engine, Qd, Fd, 200)
+            cpu_parallel_rate(engine, Qd, Fd, 200, threads)
         t = 0.0
         for _ in range(args.steps):
-            _, dt = cpu_single_rate(engine, Qd, Fd, upd)
+            _, dt = cpu_parallel_rate(engine, Qd, Fd, upd, threads)
             t += dt
-        value = (upd * args.steps / t) / args.iters  # solves/s of one core at `iters` updates per solve
-        sample = f"{upd} updates of one N={d.N} problem per step, scaled to {args.iters} updates per solve"
+        value = (threads * upd * args.steps / t) / args.iters  # solves/s at `iters` updates per solve
+        sample = (f"{threads} threads x {upd} updates of one N={d.N} problem per step, scaled to {args.iters} updates per solve")
         out.update(metric="qp_solves_per_sec", unit="solves/s", value=value, ms_per_step=1e3 * t / args.steps,
                    config={"workload": args.workload, "N": d.N, "M": d.M, "B": w["B"], "iters_per_solve": args.iters})
-    out["cpu_baseline"] = {"value": out["value"], "unit": out["unit"], "cores": 1, "kind": kind, "sample": sample}
+    out["cpu_baseline"] = {"value": out["value"], "unit": out["unit"], "cores": threads, "kind": kind, "sample": sample}
     out["e2e"] = {"value": out["value"], "unit": out["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     out["gpu_launches"] = 0
     print(json.dumps(out), flush=True)
@@ -288,7 +352,7 @@ def run_ours(args, w, rank, world, local_rank):
                            "d2h_bytes_per_step": 4 * N + st.itemsize, "ms_per_step": ms_e2e / args.steps,
                            "call": "pqp_solve_dual(host Fd -> host Y, status)"},
                       roofline={"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                                "traffic": None, "peak_source": peak_src, "kernel": kernel, "kernel_ms_per_step": k_ms,
+                                "traffic": ncu_traffic(kernel), "peak_source": peak_src, "kernel": kernel, "kernel_ms_per_step": k_ms,
                                 "bytes_per_iteration": bytes_iter, "frac_of_8TBs_nominal": achieved / 8000.0},
                       gpu_launches=int(launches), clocks=clocks)
         if rank == 0 and not args.no_cpu:
@@ -349,15 +413,13 @@ def run_ours(args, w, rank, world, local_rank):
                    "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "solves/s",
                            "h2d_bytes_per_step": int(X.nbytes), "d2h_bytes_per_step": int(Y_pin.numel() * 4 + U_pin.numel() * 4),
                            "call": "pqp_solve_batch_primal(host X -> host Y, U)"},
-                   "roofline": {"bound": "tensor", "achieved": tfl, "unit": "TFLOP/s", "kernel": s.last_kernel,
-                                "kernel_ms_per_step": k_ms, "flop_per_iteration": flop_iter,
-                                "note": "fp32-equivalent flop 4*N^2*B per iteration; the SIMT kernel's own ceiling is the fp32 FMA pipe"},
+                   "roofline": batched_roofline(s.last_kernel, tfl, k_ms, flop_iter, d.N, B, args.iters),
                    "gpu_launches": int(launches)}
         s.close()
         if w["kind"] == "batched":
             result.update(metric=batched["metric"], unit=batched["unit"], value=batched["value"], ms_per_step=batched["ms_per_step"],
-                          config=batched["config"] | {"workload": "c4"}, e2e=batched["e2e"], roofline=batched["roofline"] | {
-                              "peak": None, "frac": None, "traffic": None}, gpu_launches=batched["gpu_launches"], clocks=clocks_b)
+                          config=batched["config"] | {"workload": "c4"}, e2e=batched["e2e"], roofline=batched["roofline"],
+                          gpu_launches=batched["gpu_launches"], clocks=clocks_b)
             if rank == 0 and not args.no_cpu:
                 engine, kind = cpu_engine()
                 from oracle.oracle import Oracle

@@ -560,8 +560,8 @@ enum { BATCH_SIMT = 0, BATCH_IMMA = 1, BATCH_UMMA = 2 };
 static int batched_engine(const pqp_handle *h)
 {
 	/*
-	 * use_tensor_cores: 0 -> SIMT.  1 (default) -> the int8 kernel: exact integer accumulation in TMEM, accuracy of the fp32
-	 * oracle.  2 -> the 3xTF32 kernel: its fp32 accumulator truncates on every step, which leaves the loop
+	 * use_tensor_cores: 0 -> SIMT.  1 (default) -> the int8 kernel: exact integer accumulation in TMEM, accuracy of
+	 * PQP_CPU.c's own fp32 arithmetic.  2 -> the 3xTF32 kernel: its fp32 accumulator truncates on every step, which leaves the loop
 	 * 5-100x above the fp32 noise floor after 1000 updates, so it is opt-in only.  PQP_BATCHED=simt|imma|umma overrides.
 	 */
 	const char *e = getenv("PQP_BATCHED");

@@ -18,7 +18,7 @@
  *   sum_k q_ik y_k = (w0*2^16 + w1*2^8 + w2) * 2^(e_i-8) * 2^(f_b-22)  up to the 2^-24-level roundings of the fixed-point conversions
  * The diagonal term (Q^+-_ii + theta_i)*y_i (the largest single term, PQP_CPU.c:527,536) and F^+- are added in fp32 in the
  * epilogue, the division is IEEE, and the master copy of y stays in fp32 registers: only the tensor-core operand is quantised.
- * Accuracy measured against the float64 twin of the oracle is that of the fp32 oracle itself (tools/ozaki_emulate.py).
+ * Accuracy against a float64 run of the same algorithm is that of PQP_CPU.c's own fp32 arithmetic (tests/imma_model.py).
  *
  * It is also the cheaper contraction: 6 slice products at the int8 rate (4x tf32) = 1.5 tf32-equivalents instead of 3 (3xTF32),
  * 3 bytes per operand element instead of 8.
