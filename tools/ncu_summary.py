@@ -1,4 +1,6 @@
-"""Summarise an .ncu-rep (read here, no GPU needed): python tools/ncu_summary.py <rep> <out.txt> [title]"""
+"""Summarise an .ncu-rep (read here, no GPU needed): python tools/ncu_summary.py <rep> <out.txt> [title] [bench_kernel_name]
+With bench_kernel_name, also records dram bytes (read+write) per launch of the first captured kernel under that name in
+profiles/ncu_traffic.json, which bench.py reports as roofline.traffic."""
 import csv
 import subprocess
 import sys
@@ -27,3 +29,17 @@ with open(out, "w") as f:
                     continue
                 f.write(f"{h:75s} {v:>22s} {u}\n")
 print(open(out).read()[:6000])
+
+if len(sys.argv) > 4:
+    import json, os
+    name = sys.argv[4]
+    r = rows[2]
+    def col(metric):
+        i = hdr.index(metric)
+        v, u = float(r[i].replace(",", "")), units[i].lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(u, 1)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    d = json.load(open(path)) if os.path.exists(path) else {}
+    d[name] = col("dram__bytes_read.sum") + col("dram__bytes_write.sum")
+    json.dump(d, open(path, "w"), indent=1, sort_keys=True)
+    print("traffic", name, d[name])
