@@ -95,8 +95,10 @@ typedef struct pqp_opts {
 	int max_iters;     /* cap for run-to-tolerance mode                         default 100000 */
 	int check_every;   /* run-to-tolerance: test every this many iterations     default 8    */
 	int batch_capacity;/* problems the workspace is sized for (grows on demand) default 1    */
-	int use_tensor_cores; /* FAST mode: 0 fp32 SIMT everywhere; 1 (default) tcgen05 3xTF32 for the setup GEMMs;
-			       * 2 also the batched loop on tcgen05 (faster, but above the 1e-5 parity tolerance: opt-in) */
+	int use_tensor_cores; /* FAST mode: 0 fp32 SIMT everywhere; 1 (default) tcgen05: 3xTF32 for the setup GEMMs and int8 digit
+			       * planes with exact int32 accumulation for the batched loop (accuracy of PQP_CPU.c's own fp32);
+			       * 2 the batched loop on 3xTF32 instead (its truncating accumulator leaves it above the 1e-5 parity
+			       * tolerance after many updates: opt-in, for comparison) */
 	int l2_persist;    /* 1: pin as much of Q as the device allows in L2 (GEMV regime) default 1 */
 } pqp_opts;
 
@@ -171,7 +173,9 @@ void pqp_destroy(pqp_handle *h);
  *   iters <= 0: until the stop test on (min_slack, gap, Jd) passes or opts.max_iters.
  * X [B x nState] (ignored when nState == 0), D [B x nDisH] or NULL (problem's D for all),
  * Y0 [B x N] or NULL, Y [B x N] out, st [B] out or NULL.  X, D, Y0, Y: host or device.
- * B == 1 runs the persistent GEMV kernel, B > 1 the batched kernel.
+ * B == 1 runs the persistent GEMV kernel, B > 1 the batched kernel (tensor cores), which in run-to-tolerance mode evaluates
+ * the stop test per problem every opts.check_every updates and freezes each problem at exactly the y that passed: its result
+ * equals the fixed-count solve with iters = st[b].iters, whatever its batch mates do.
  */
 int pqp_solve_batch(pqp_handle *h, const float *X, const float *D, int B, int iters, const float *Y0,
 		    float *Y, pqp_status *st);
@@ -207,7 +211,7 @@ void *pqp_get_stream(pqp_handle *h);
 float pqp_last_solve_ms(pqp_handle *h);
 /* how many of this library's kernels the handle has launched so far */
 long long pqp_launch_count(pqp_handle *h);
-/* name of the iteration kernel the last solve used ("gemv_stream", "gemv_strict", "batched_simt", "batched_umma", ...) */
+/* name of the iteration kernel the last solve used ("gemv_tma_stream", "gemv_strict", "batched_imma", "batched_simt", ...) */
 const char *pqp_last_kernel(pqp_handle *h);
 /* device copy of Qd (row stride = *ld floats), for zero-copy callers; valid until pqp_destroy */
 const float *pqp_device_qd(pqp_handle *h, int *ld);

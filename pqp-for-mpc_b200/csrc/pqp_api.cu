@@ -617,11 +617,13 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 	const int N = h->d.N;
 	const int strict = h->o.order == PQP_ORDER_STRICT;
 	const int want_status = st != NULL;
-	const float *Md = (want_status && h->have_fp_model) ? h->Md : NULL;
+	const float *Md = ((want_status || iters <= 0) && h->have_fp_model) ? h->Md : NULL; /* tolerance mode needs Jd, hence Md */
 	h->ev_valid = 0;
 
 	const int engine = batched_engine(h);
-	const int batched = B > 1 && iters > 0 && !strict && (engine != BATCH_SIMT || pqp_batched_simt_supported(N));
+	/* fixed count: any batched engine; run-to-tolerance (iters <= 0): the int8 engine evaluates the stop test per problem itself */
+	const int batched = B > 1 && !strict &&
+			    (iters > 0 ? (engine != BATCH_SIMT || pqp_batched_simt_supported(N)) : engine == BATCH_IMMA);
 	if (batched) {
 		int rc = engine == BATCH_IMMA ? ensure_imma_tiles(h) : (engine == BATCH_UMMA ? ensure_umma_tiles(h) : ensure_batched_operands(h));
 		if (rc) return rc;
@@ -640,7 +642,11 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			int cluster = 1;
 			if (getenv("PQP_IMMA_CLUSTER")) cluster = atoi(getenv("PQP_IMMA_CLUSTER"));
 			if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) cluster = 1;
-			CK(pqp_launch_batched_imma(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, nb, cluster, h->smem_optin, h->stream));
+			pqp_imma_tol t;
+			t.max_iters = h->o.max_iters; t.check_every = h->o.check_every;
+			t.erc = h->o.erc; t.eac = h->o.eac; t.eaj = h->o.eaj; t.erj = h->o.erj;
+			t.Kp = h->Kp; t.Md = Md; t.status = h->st;
+			CK(pqp_launch_batched_imma(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, nb, cluster, h->smem_optin, &t, h->stream));
 			h->last_kernel = "batched_imma";
 		} else if (engine == BATCH_UMMA) {
 			int cluster = 4;
@@ -655,7 +661,7 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 		CK(cudaEventRecord(h->ev1, h->stream));
 		h->ev_valid = 1;
 		h->launches++;
-		if (want_status) {
+		if (want_status && iters > 0) { /* in tolerance mode the kernel wrote the status of every problem itself */
 			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, Md, h->Kp, h->o.erc, h->o.eac, B, iters, h->stream));
 			h->launches++;
 		}
@@ -714,7 +720,7 @@ int pqp_solve_batch(pqp_handle *h, const float *X, const float *D, int B, int it
 	CK(cudaSetDevice(h->device));
 	int rc = ensure_capacity(h, B);
 	if (rc) return rc;
-	if ((rc = form_linear_terms(h, X, D, B, st != NULL))) return rc;
+	if ((rc = form_linear_terms(h, X, D, B, st != NULL || iters <= 0))) return rc;
 	if ((rc = run_loop(h, B, iters, Y0, Y, st))) return rc;
 	CK(cudaStreamSynchronize(h->stream));
 	return PQP_OK;
@@ -777,7 +783,7 @@ int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B,
 	CK(cudaSetDevice(h->device));
 	int rc = ensure_capacity(h, B);
 	if (rc) return rc;
-	if ((rc = form_linear_terms(h, X, D, B, st != NULL))) return rc;
+	if ((rc = form_linear_terms(h, X, D, B, st != NULL || iters <= 0))) return rc;
 	if ((rc = run_loop(h, B, iters, Y0, Y, st))) return rc;
 	if ((rc = recover_on_device(h, h->Y, h->d.N, NULL, B, U))) return rc;
 	CK(cudaStreamSynchronize(h->stream));

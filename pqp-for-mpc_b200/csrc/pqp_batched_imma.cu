@@ -233,6 +233,14 @@ struct BiParams {
 	int dbuf;                    /* 1: two plane buffers -> new digits are stored speculatively while the MMAs still read the old ones */
 	int stages;                  /* ring depth */
 	uint32_t b_sbo;              /* B operand: byte stride between 16-problem groups = Kpad*16 */
+	/* run-to-tolerance (iters <= 0): every check_every updates one EVALUATION pass (same MMAs, no update) forms g = den - num =
+	 * Qd y + Fd per row and reduces the stop test of terminate() (PQP_CPU.c:673-687) per problem; a problem that
+	 * passes is frozen at exactly that y.  All passes of a problem before it freezes are the fixed-count passes. */
+	int max_iters, check_every;
+	float erc, eac, eaj, erj;
+	const float *Kp;             /* [N] or NULL */
+	const float *Md;             /* [B] or NULL */
+	pqp_status *status;          /* [B], written in tolerance mode */
 	int dbg;                     /* experiment switches (PQP_IMMA_DBG): 2 skip all MMAs, 4 skip epilogue math, 8 print wait-time profile */
 	long long *prof;             /* dbg & 8: [8] cycle counters of CTA 0 (see PROF_*) */
 };
@@ -240,7 +248,7 @@ struct BiParams {
 /*
  * shared memory: ring [stages][ksc*BI_CHUNK] | B planes [3][NB/16][Kpad/8][8][16 B] | smax[2][NB] | iscale[2][NB] | barriers
  */
-template <int NB, int PW>
+template <int NB, int PW, bool TOL>
 __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(const BiParams p)
 {
 	constexpr int EW = 4 * (NB / PW);    /* epilogue warps: 4 lane quarters x NB/PW problem groups of PW problems per thread */
@@ -268,12 +276,16 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 	uint64_t *tmem_full = empty + p.stages;   /* [2] */
 	uint64_t *tmem_empty = tmem_full + 2;     /* [2] */
 	uint64_t *b_ready = tmem_empty + 2;
-	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(b_ready + 1);
+	uint64_t *decided = b_ready + 1;          /* tolerance mode: the stop decision of an evaluation pass is in *stop_flag */
+	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(decided + 1);
+	uint32_t *stop_flag = tmem_slot + 1;
+	uint32_t *frozen = stop_flag + 1;         /* [NB] */
+	float *part = reinterpret_cast<float *>(frozen + NB); /* [EW][PW][5] per-warp partial sums of an evaluation pass */
+	constexpr bool tol = TOL; /* run-to-tolerance is a separate instantiation: the fixed-count kernel carries none of its registers */
 
 	const int units_per_iter = 2 * MT;
 	const int chunks_per_unit = NKS / p.ksc;
 	const int chunks_per_iter = units_per_iter * chunks_per_unit;
-	const long long total_chunks = (long long)chunks_per_iter * p.iters;
 	const int b0 = blockIdx.x * NB;
 	const bool prof_on = (p.dbg & 8) && p.prof && blockIdx.x == 0;
 	long long prof_acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -288,9 +300,12 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 			umma::mbar_init(&tmem_empty[i], ETHREADS);
 		}
 		umma::mbar_init(b_ready, ETHREADS);
+		umma::mbar_init(decided, ETHREADS);
+		*stop_flag = 0u;
 		umma::mbar_fence_init();
 	}
 	if (tid < 2 * NB) smax[tid] = 0u;
+	if (tid < NB) frozen[tid] = (b0 + tid < p.B) ? 0u : 1u; /* padding problems never hold the CTA back */
 	for (uint32_t i = tid; i < nbuf * pbuf_bytes / 16u; i += blockDim.x) reinterpret_cast<uint4 *>(Bpl)[i] = make_uint4(0u, 0u, 0u, 0u);
 	umma::fence_proxy_async(); /* K padding of the planes is never rewritten: make the zeros visible to the tensor core's reads */
 	if (warp == 1) umma::tmem_alloc(tmem_slot, TMEM_COLS);
@@ -304,22 +319,37 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 		/* ================= producer: A chunks through the ring (whole warp, one elected lane issues) ================= */
 		int st = 0;
 		uint32_t ph = 0;
-		int within = 0;
-		for (long long c = 0; c < total_chunks; c++) {
-			PROF_T(tw);
-			umma::mbar_wait(&empty[st], ph ^ 1u);
-			PROF_ADD(PROF_PROD_WAIT_EMPTY, tw);
-			if (elect_one()) {
-				umma::mbar_arrive_expect_tx(&full[st], stage_bytes);
-				const unsigned char *src = p.Atiles + (size_t)within * stage_bytes;
-				if (CS == 1)
-					bulk_g2s_plain(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st]);
-				else if ((uint32_t)(c % CS) == crank)
-					bulk_g2s_mcast(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st], cmask);
+		long long c = 0;
+		int upd = 0, since = 0;
+		uint32_t n_eval = 0;
+		for (;;) {
+			if (!tol && upd == p.iters) break;
+			const bool ev = tol && (since == p.check_every || upd >= p.max_iters);
+			for (int within = 0; within < chunks_per_iter; within++, c++) {
+				PROF_T(tw);
+				umma::mbar_wait(&empty[st], ph ^ 1u);
+				PROF_ADD(PROF_PROD_WAIT_EMPTY, tw);
+				if (elect_one()) {
+					umma::mbar_arrive_expect_tx(&full[st], stage_bytes);
+					const unsigned char *src = p.Atiles + (size_t)within * stage_bytes;
+					if (CS == 1)
+						bulk_g2s_plain(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st]);
+					else if ((uint32_t)(c % CS) == crank)
+						bulk_g2s_mcast(ring + (size_t)st * stage_bytes, src, stage_bytes, &full[st], cmask);
+				}
+				__syncwarp();
+				if (++st == p.stages) { st = 0; ph ^= 1u; }
 			}
-			__syncwarp();
-			if (++within == chunks_per_iter) within = 0;
-			if (++st == p.stages) { st = 0; ph ^= 1u; }
+			if (ev) {
+				/* no copies may be in flight into a CTA that is about to exit: wait for the decision before running ahead */
+				since = 0;
+				umma::mbar_wait(decided, n_eval & 1u);
+				n_eval++;
+				if (*reinterpret_cast<volatile uint32_t *>(stop_flag)) break;
+			} else {
+				upd++;
+				since++;
+			}
 		}
 		if (prof_on && lane == 0) p.prof[PROF_PROD_WAIT_EMPTY] = prof_acc[PROF_PROD_WAIT_EMPTY];
 	} else if (warp == 1) {
@@ -330,10 +360,14 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 		int st = 0;
 		uint32_t ph = 0;
 		long long unit = 0;
+		int upd = 0, since = 0;
+		uint32_t n_eval = 0, pbi = 0; /* pbi: plane buffer the MMAs of this pass read */
 		PROF_T(tm0);
-		for (int it = 0; it < p.iters; it++) {
+		for (long long pass = 0;; pass++) {
+			if (!tol && upd == p.iters) break;
+			const bool ev = tol && (since == p.check_every || upd >= p.max_iters);
 			PROF_T(tb);
-			umma::mbar_wait(b_ready, (uint32_t)(it & 1)); /* digit planes of this iteration are in place */
+			umma::mbar_wait(b_ready, (uint32_t)(pass & 1)); /* digit planes of this pass are in place */
 			PROF_ADD(PROF_MMA_WAIT_BREADY, tb);
 			umma::tc_fence_after();
 			for (int u = 0; u < units_per_iter; u++, unit++) {
@@ -351,7 +385,7 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 					if (elect_one()) {
 						/* only the 14-bit start-address field of the descriptors moves: +768 per 12 KB of ring, +32 per K step */
 						const uint64_t da = a_desc0 + (uint64_t)((uint32_t)st * (stage_bytes >> 4));
-						const uint64_t db = b_desc0 + (uint64_t)((uint32_t)(ch * p.ksc) * (4u * BI_B_LBO >> 4) + ((p.dbuf && (it & 1)) ? (pbuf_bytes >> 4) : 0u));
+						const uint64_t db = b_desc0 + (uint64_t)((uint32_t)(ch * p.ksc) * (4u * BI_B_LBO >> 4) + (pbi ? (pbuf_bytes >> 4) : 0u));
 						if (!(p.dbg & 2)) {
 							if (p.ksc == 3) mma_i8_step3(d, d + NB, d + 2 * NB, da, db, id3, id2, id1, ch ? 1u : 0u);
 							else mma_i8_step(d, d + NB, d + 2 * NB, da, db, id3, id2, id1, ch ? 1u : 0u);
@@ -364,6 +398,16 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 				}
 				if (elect_one()) umma::mma_commit(&tmem_full[buf]);
 				__syncwarp();
+			}
+			if (ev) {
+				since = 0;
+				umma::mbar_wait(decided, n_eval & 1u);
+				n_eval++;
+				if (*reinterpret_cast<volatile uint32_t *>(stop_flag)) break;
+			} else {
+				upd++;
+				since++;
+				if (p.dbuf) pbi ^= 1u;
 			}
 		}
 		PROF_ADD(PROF_MMA_TOTAL, tm0);
@@ -476,12 +520,21 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 		requantise(1, 0u, false, 0);
 		umma::mbar_arrive(b_ready);
 
-		long long pair = 0; /* (iteration, M tile) counter: completion index of tmem_full[0] and [1] */
+		long long pair = 0; /* (pass, M tile) counter: completion index of tmem_full[0] and [1] */
+		int upd = 0, since = 0;
+		uint32_t n_eval = 0, pbi = 0;
 		PROF_T(te0);
-		for (int it = 0; it < p.iters; it++) {
-			const int par_in = (it & 1) ^ 1; /* scales the planes of this iteration were quantised with */
-			const int par_out = it & 1;
+		for (;;) {
+			if (!tol && upd == p.iters) break;
+			const bool ev = tol && (since == p.check_every || upd >= p.max_iters);
+			const int par_out = upd & 1;     /* max / scale slots the update of this pass fills */
+			const int par_in = par_out ^ 1;  /* scales the planes being read were quantised with */
 			float isc[PW];
+			uint32_t fz = 0;                 /* problems of this thread that are frozen (tolerance mode) */
+			if (tol) {
+#pragma unroll
+				for (int j = 0; j < PW; j++) fz |= (frozen[pb + j] ? 1u : 0u) << j;
+			}
 #pragma unroll
 			for (int mt = 0; mt < BI_MAX_MT; mt++) {
 				if (mt < MT) {
@@ -490,6 +543,7 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 #pragma unroll
 					for (int j = 0; j < PW; j++) fd[j] = (i < N && b0 + pb + j < p.B) ? __ldg(p.Fd + (size_t)(b0 + pb + j) * N + i) : 1.0f;
 					float sn[PW];
+					float e_viol[PW], e_min[PW], e_gap[PW], e_jd[PW], e_kkt[PW]; /* evaluation pass only */
 #pragma unroll
 					for (int mat = 0; mat < 2; mat++) {
 						PROF_T(tw);
@@ -497,12 +551,14 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 						PROF_ADD(PROF_EPI_WAIT_TMEM, tw);
 						umma::tc_fence_after();
 						if (mt == 0 && mat == 0) {
-							/* first unit of the iteration: every thread is past the previous requantise -> safe to read the
-							 * inverse scales and to reset the max slots the NEXT requantise will use */
+							/* first unit of the pass: every thread is past the previous requantise -> safe to read the inverse
+							 * scales and (update pass) to reset the max slots the NEXT requantise will use */
 #pragma unroll
 							for (int j = 0; j < PW; j++) isc[j] = iscale[par_in * NB + pb + j];
-							if (et < NB) smax[par_out * NB + et] = 0u;
-							named_bar_sync(2, ETHREADS);
+							if (!ev) {
+								if (et < NB) smax[par_out * NB + et] = 0u;
+								named_bar_sync(2, ETHREADS);
+							}
 						}
 						const uint32_t col = tmem + lane_addr + (uint32_t)mat * UNIT_COLS + (uint32_t)pb;
 						int w0[PW], w1[PW], w2[PW];
@@ -515,6 +571,8 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 						const float rs = mat == 0 ? rc[mt].z : rc[mt].w;
 						const float dg = mat == 0 ? rc[mt].x : rc[mt].y;
 						if (!(p.dbg & 4)) {
+							float tol_i = 0.0f;
+							if (ev && mat == 1) tol_i = (p.Kp && i < N) ? fmaxf(p.erc * __ldg(p.Kp + i), p.eac) : p.eac;
 #pragma unroll
 							for (int j = 0; j < PW; j++) {
 								/* (w0*2^16 + w1*2^8 + w2) * 2^(e-8) * 2^(f-22): two fused roundings, then exact scalings */
@@ -525,30 +583,105 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 									sn[j] = __fadd_rn(__fadd_rn(S, dy), fmaxf(-fd[j], 0.0f));
 								} else {
 									const float den = __fadd_rn(__fadd_rn(S, dy), fmaxf(fd[j], 0.0f));
-									if (i < N) y[mt][j] = __fmul_rn(__fdiv_rn(sn[j], den), y[mt][j]);
+									if (!ev) {
+										if (i < N && !((fz >> j) & 1u)) y[mt][j] = __fmul_rn(__fdiv_rn(sn[j], den), y[mt][j]);
+									} else {
+										/* g = den - num = Qd y + Fd: slack of constraint i at U(y) */
+										const float g = __fsub_rn(den, sn[j]), yi = y[mt][j];
+										const bool live = i < N;
+										e_viol[j] = live ? -g - tol_i : -INFINITY;
+										e_min[j] = live ? g : INFINITY;
+										e_gap[j] = live ? __fmul_rn(yi, g) : 0.0f;
+										e_jd[j] = live ? __fmul_rn(yi, 0.5f * (g + fd[j])) : 0.0f;
+										e_kkt[j] = live ? fabsf(fminf(yi, g)) : 0.0f;
+									}
 								}
 							}
 						}
 					}
 					pair++;
-					/* this tile's new duals are final: publish their maxima, and (two plane buffers) store their digits right away
-					 * with the scales of the previous maxima -- almost always the exponent the exact maxima will confirm */
-					publish_tile_max(y[mt], smax + par_out * NB);
-					if (p.dbuf) {
-						float scp[PW];
+					if (!ev) {
+						/* this tile's new duals are final: publish their maxima, and (two plane buffers) store their digits right away
+						 * with the scales of the previous maxima -- almost always the exponent the exact maxima will confirm */
+						publish_tile_max(y[mt], smax + par_out * NB);
+						if (p.dbuf) {
+							float scp[PW];
+#pragma unroll
+							for (int j = 0; j < PW; j++) {
+								float iscp;
+								problem_scales(smax[par_in * NB + pb + j], scp[j], iscp);
+							}
+							store_tile(mt, y[mt], scp, pbi ^ 1u);
+						}
+					} else {
+						/* fold this tile's rows: fixed xor tree over the 32 rows of the warp, tiles in ascending order */
 #pragma unroll
 						for (int j = 0; j < PW; j++) {
-							float iscp;
-							problem_scales(smax[par_in * NB + pb + j], scp[j], iscp);
+							float v = e_viol[j], m = e_min[j], ga = e_gap[j], jd = e_jd[j], kk = e_kkt[j];
+#pragma unroll
+							for (int o = 16; o; o >>= 1) {
+								v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+								m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+								ga = __fadd_rn(ga, __shfl_xor_sync(0xffffffffu, ga, o));
+								jd = __fadd_rn(jd, __shfl_xor_sync(0xffffffffu, jd, o));
+								kk = fmaxf(kk, __shfl_xor_sync(0xffffffffu, kk, o));
+							}
+							if (lane == 0) {
+								float *pp = part + ((size_t)ew * PW + j) * 5;
+								if (mt == 0) {
+									pp[0] = v; pp[1] = m; pp[2] = ga; pp[3] = jd; pp[4] = kk;
+								} else {
+									pp[0] = fmaxf(pp[0], v); pp[1] = fminf(pp[1], m); pp[2] = __fadd_rn(pp[2], ga);
+									pp[3] = __fadd_rn(pp[3], jd); pp[4] = fmaxf(pp[4], kk);
+								}
+							}
 						}
-						store_tile(mt, y[mt], scp, (uint32_t)(par_out ^ 1) & 1u);
 					}
 				}
 			}
-			PROF_T(tq);
-			requantise(par_out, p.dbuf ? ((uint32_t)(it + 1) & 1u) : 0u, p.dbuf != 0, par_in);
-			umma::mbar_arrive(b_ready);
-			PROF_ADD(PROF_EPI_REQUANT, tq);
+			if (!ev) {
+				PROF_T(tq);
+				requantise(par_out, p.dbuf ? (pbi ^ 1u) : 0u, p.dbuf != 0, par_in);
+				umma::mbar_arrive(b_ready);
+				PROF_ADD(PROF_EPI_REQUANT, tq);
+				upd++;
+				since++;
+				if (p.dbuf) pbi ^= 1u;
+			} else {
+				/* the stop test of terminate(), per problem, on the reductions of g (no extra matrix traffic) */
+				named_bar_sync(1, ETHREADS);
+				if (et < NB && !frozen[et] ) {
+					const int cgp = et / PW, j = et % PW;
+					float v = -INFINITY, m = INFINITY, ga = 0.0f, jd = 0.0f, kk = 0.0f;
+					for (int w = 0; w < 4; w++) { /* the four lane-quarter warps of this problem group, fixed order */
+						const float *pp = part + ((size_t)(cgp * 4 + w) * PW + j) * 5;
+						v = fmaxf(v, pp[0]); m = fminf(m, pp[1]); ga = __fadd_rn(ga, pp[2]); jd = __fadd_rn(jd, pp[3]); kk = fmaxf(kk, pp[4]);
+					}
+					const float Jd = jd + (p.Md ? 0.5f * p.Md[b0 + et] : 0.0f);
+					const bool conv = v <= 0.0f && fabsf(ga) <= p.eaj && fabsf(ga) <= p.erj * fabsf(Jd);
+					/* a problem the reference itself drives to 0/0 (all-NaN duals) can never pass: retire it unconverged
+					 * instead of holding its 31 batch mates until max_iters */
+					const bool dead = !(fabsf(ga) <= 3.0e38f) || !(fabsf(jd) <= 3.0e38f);
+					if (conv || dead || upd >= p.max_iters) {
+						pqp_status o;
+						o.iters = upd; o.converged = conv ? 1 : 0; o.min_slack = m; o.gap = ga; o.Jd = Jd; o.kkt = kk;
+						p.status[b0 + et] = o;
+					}
+					if (conv || dead) frozen[et] = 1u;
+				}
+				named_bar_sync(1, ETHREADS);
+				if (et == 0) {
+					uint32_t all = 1u;
+					for (int b = 0; b < NB; b++) all &= frozen[b];
+					*stop_flag = (all || upd >= p.max_iters) ? 1u : 0u;
+				}
+				since = 0;
+				umma::mbar_arrive(decided);
+				umma::mbar_wait(decided, n_eval & 1u);
+				n_eval++;
+				if (*reinterpret_cast<volatile uint32_t *>(stop_flag)) break;
+				umma::mbar_arrive(b_ready); /* the planes are unchanged: the next pass may start */
+			}
 		}
 		PROF_ADD(PROF_EPI_TOTAL, te0);
 		if (prof_on && et == 0)
@@ -647,13 +780,14 @@ cudaError_t pqp_launch_build_imma_tiles(void *tiles, void *rowc, const float *Q,
 	return cudaGetLastError();
 }
 
-template <int NB, int PW>
+template <int NB, int PW, bool TOL>
 static cudaError_t launch_imma(const BiParams &p0, int cluster, size_t smem_optin, cudaStream_t s)
 {
 	BiParams p = p0;
 	const size_t pbuf = 3 * (size_t)(NB / 16) * p.b_sbo;
 	const size_t stage_bytes = (size_t)p.ksc * BI_CHUNK;
-	const size_t misc = 4 * NB * sizeof(uint32_t) + 64 /* barriers besides the ring's */ + 16;
+	const size_t misc = 4 * NB * sizeof(uint32_t) + 64 /* barriers besides the ring's */ + 32 + NB * sizeof(uint32_t) +
+			    (size_t)(4 * NB) * 5 * sizeof(float) /* evaluation partials [EW][PW][5], EW*PW = 4*NB */;
 	/* two plane buffers when at least three ring stages still fit beside them */
 	p.dbuf = (2 * pbuf + misc + 3 * (stage_bytes + 16) + 1024 <= smem_optin) ? 1 : 0;
 	if (getenv("PQP_IMMA_DBUF")) p.dbuf = p.dbuf && atoi(getenv("PQP_IMMA_DBUF")) != 0;
@@ -667,11 +801,11 @@ static cudaError_t launch_imma(const BiParams &p0, int cluster, size_t smem_opti
 	if (stages < 2) return cudaErrorInvalidConfiguration;
 	p.stages = stages;
 	const size_t smem = (size_t)stages * stage_bytes + fixed + (size_t)stages * 16;
-	cudaError_t e = cudaFuncSetAttribute(batched_imma_kernel<NB, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	cudaError_t e = cudaFuncSetAttribute(batched_imma_kernel<NB, PW, TOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	if (cluster < 1) cluster = 1;
 	if (cluster > 8) {
-		e = cudaFuncSetAttribute(batched_imma_kernel<NB, PW>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+		e = cudaFuncSetAttribute(batched_imma_kernel<NB, PW, TOL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
 		if (e != cudaSuccess) return e;
 	}
 	int ctas = (p.B + NB - 1) / NB;
@@ -689,11 +823,11 @@ static cudaError_t launch_imma(const BiParams &p0, int cluster, size_t smem_opti
 	attr[0].val.clusterDim.z = 1;
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
-	return cudaLaunchKernelEx(&cfg, batched_imma_kernel<NB, PW>, p);
+	return cudaLaunchKernelEx(&cfg, batched_imma_kernel<NB, PW, TOL>, p);
 }
 
 cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters, int nb,
-				    int cluster, size_t smem_optin, cudaStream_t s)
+				    int cluster, size_t smem_optin, const pqp_imma_tol *tolp, cudaStream_t s)
 {
 	BiParams p;
 	memset(&p, 0, sizeof p);
@@ -707,6 +841,15 @@ cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, 
 	imma_geometry(N, &p.MT, &p.NKS, &p.ksc);
 	p.b_sbo = (uint32_t)(p.NKS * 32) * 16u;
 	p.dbg = getenv("PQP_IMMA_DBG") ? atoi(getenv("PQP_IMMA_DBG")) : 0;
+	if (iters <= 0) {
+		if (!tolp || !tolp->status) return cudaErrorInvalidValue;
+		p.iters = 0;
+		p.max_iters = tolp->max_iters;
+		p.check_every = tolp->check_every > 0 ? tolp->check_every : 1;
+		p.erc = tolp->erc; p.eac = tolp->eac; p.eaj = tolp->eaj; p.erj = tolp->erj;
+		p.Kp = tolp->Kp; p.Md = tolp->Md; p.status = tolp->status;
+		cluster = 1; /* CTAs stop independently */
+	}
 	static long long *prof_dev = NULL;
 	if (p.dbg & 8) {
 		if (!prof_dev) cudaMalloc((void **)&prof_dev, 8 * sizeof(long long));
@@ -716,8 +859,11 @@ cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, 
 	/* PW = problems per epilogue thread: 8 doubles the epilogue warps of the 32-problem tile (16 instead of 8), which is what
 	 * hides the latency of its dependent fp32 chain (division, conversions) behind the tensor pipe */
 	const int pw = getenv("PQP_IMMA_PW") ? atoi(getenv("PQP_IMMA_PW")) : 8;
-	cudaError_t e = nb == 64 ? launch_imma<64, 16>(p, cluster, smem_optin, s)
-				 : (pw == 16 ? launch_imma<32, 16>(p, cluster, smem_optin, s) : launch_imma<32, 8>(p, cluster, smem_optin, s));
+	cudaError_t e;
+	if (iters <= 0) e = launch_imma<32, 8, true>(p, cluster, smem_optin, s);
+	else if (nb == 64) e = launch_imma<64, 16, false>(p, cluster, smem_optin, s);
+	else if (pw == 16) e = launch_imma<32, 16, false>(p, cluster, smem_optin, s);
+	else e = launch_imma<32, 8, false>(p, cluster, smem_optin, s);
 	if ((p.dbg & 8) && e == cudaSuccess) {
 		long long h[8];
 		cudaStreamSynchronize(s);

@@ -108,8 +108,16 @@ int pqp_batched_imma_supported(int N);
 size_t pqp_batched_imma_tiles_bytes(int N);
 size_t pqp_batched_imma_rowc_bytes(int N);
 cudaError_t pqp_launch_build_imma_tiles(void *tiles, void *rowc, const float *Q, int ldq, const float *theta, int N, cudaStream_t s);
+/* iters <= 0: run to the stop test of terminate() (tol != NULL), checked every check_every updates, per problem */
+typedef struct pqp_imma_tol {
+	int max_iters, check_every;
+	float erc, eac, eaj, erj;
+	const float *Kp;    /* [N] or NULL */
+	const float *Md;    /* [B] or NULL */
+	pqp_status *status; /* [B] device */
+} pqp_imma_tol;
 cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters, int nb,
-				    int cluster, size_t smem_optin, cudaStream_t s);
+				    int cluster, size_t smem_optin, const pqp_imma_tol *tol, cudaStream_t s);
 #define PQP_BATCH_KPAD 16
 #define PQP_BATCH_IPAD 128
 

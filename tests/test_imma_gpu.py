@@ -120,3 +120,39 @@ def test_engines_agree_within_tolerance(pqp, oracle32, oracle64):
             e_gf, e_gd = relerr(out[name][b], y32), relerr(out[name][b], y64)
             assert e_gf <= TOL or (e_gf <= 2 * e_fd and e_gd <= max(2 * e_fd, TOL)), (name, b, e_gf, e_gd, e_fd)
         assert relerr(out["umma"][b], y32) <= 1e-3
+
+
+def test_batched_run_to_tolerance(pqp):
+    """iters <= 0 with B > 1: the int8 kernel evaluates the stop test of terminate() (PQP_CPU.c:673-687, on g = Qd y + Fd,
+    SURVEY 3.3) per problem every check_every updates and freezes a problem at exactly the y that passed.  Properties:
+    a problem's result is bit-identical to the fixed-count run stopped at its own iteration count; the single-problem kernel
+    stops at (or within one check of) the same count; the reported status is the one of that y."""
+    prob, d, X = _mpc(2024, 6, 5, 2, 70)
+    with pqp.Solver(d, prob, batch_capacity=70, eaj=1e-3, erj=1e-6, check_every=8, max_iters=20000) as s:
+        Y, U, st = s.solve(X, iters=0, primal=True)
+        assert s.last_kernel == "batched_imma"
+        assert st["converged"].all() and np.all(st["iters"] % 8 == 0) and st["iters"].min() >= 8 and st["iters"].max() < 20000
+        assert np.all(np.abs(st["gap"]) <= 1e-3) and np.all(st["min_slack"] >= -1e-3)
+        for b in (0, 35, 69):
+            Yf, _, stf = s.solve(X, iters=int(st["iters"][b]))
+            assert np.array_equal(Yf[b], Y[b])
+            assert abs(stf["Jd"][b] - st["Jd"][b]) <= 1e-5 * abs(st["Jd"][b]) + 1e-3
+            assert abs(stf["gap"][b] - st["gap"][b]) <= 2e-2 and abs(stf["kkt"][b] - st["kkt"][b]) <= 1e-3
+        for b in (0, 69):
+            Y1, _, st1 = s.solve(X[b][None], iters=0)
+            assert s.last_kernel.startswith("gemv_")
+            assert st1["converged"][0] == 1 and abs(int(st1["iters"][0]) - int(st["iters"][b])) <= 8
+            assert relerr(Y1[0], Y[b]) <= 1e-4
+
+
+def test_batched_run_to_tolerance_retires_degenerate_states(pqp):
+    """C4 shape: states on which the reference itself ends in 0/0 are retired unconverged; the others converge and stop early."""
+    prob, d, X = _mpc(2024, 30, 12, 4, 1100)
+    with pqp.Solver(d, prob, batch_capacity=1100, eaj=1e-2, erj=1e-6, check_every=16, max_iters=6000) as s:
+        Y, _, st = s.solve(X, iters=0)
+        nan_states = ~np.isfinite(Y).all(axis=1)
+        assert nan_states.sum() >= 1 and not st["converged"][nan_states].any()   # state 1068 is one of them (test_c4_full_size_properties)
+        assert st["iters"][nan_states].max() < 6000
+        good = ~nan_states
+        assert st["converged"][good].mean() > 0.9
+        assert np.median(st["iters"][good]) < 3000
