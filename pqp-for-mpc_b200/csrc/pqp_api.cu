@@ -642,12 +642,19 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			int cluster = 1;
 			if (getenv("PQP_IMMA_CLUSTER")) cluster = atoi(getenv("PQP_IMMA_CLUSTER"));
 			if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) cluster = 1;
+			const int pair = iters > 0 && B > 32 && pqp_batched_imma_pair_supported(N) &&
+					 (getenv("PQP_IMMA_PAIR") ? atoi(getenv("PQP_IMMA_PAIR")) != 0 : 0);
+			if (pair) {
+				CK(pqp_launch_batched_imma_pair(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, h->smem_optin, h->stream));
+				h->last_kernel = "batched_imma_pair";
+			} else {
 			pqp_imma_tol t;
 			t.max_iters = h->o.max_iters; t.check_every = h->o.check_every;
 			t.erc = h->o.erc; t.eac = h->o.eac; t.eaj = h->o.eaj; t.erj = h->o.erj;
 			t.Kp = h->Kp; t.Md = Md; t.status = h->st;
 			CK(pqp_launch_batched_imma(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, nb, cluster, h->smem_optin, &t, h->stream));
 			h->last_kernel = "batched_imma";
+			}
 		} else if (engine == BATCH_UMMA) {
 			int cluster = 4;
 			if (getenv("PQP_UMMA_CLUSTER")) cluster = atoi(getenv("PQP_UMMA_CLUSTER"));

@@ -118,6 +118,12 @@ typedef struct pqp_imma_tol {
 } pqp_imma_tol;
 cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters, int nb,
 				    int cluster, size_t smem_optin, const pqp_imma_tol *tol, cudaStream_t s);
+/* M tiles, padded K steps and K steps per ring stage of the digit-plane tile array */
+void pqp_imma_geometry(int N, int *MT, int *NKS, int *ksc);
+/* the same loop with the rows of Q split over a CTA pair sharing 64 problems (pqp_batched_imma_pair.cu); fixed count only */
+int pqp_batched_imma_pair_supported(int N);
+cudaError_t pqp_launch_batched_imma_pair(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters,
+					 size_t smem_optin, cudaStream_t s);
 #define PQP_BATCH_KPAD 16
 #define PQP_BATCH_IPAD 128
 
