@@ -77,11 +77,13 @@ def batched_roofline(kernel, tfl, k_ms, flop_iter, N, B, iters):
     out = {"bound": "tensor", "achieved": tfl, "peak": peak, "unit": "TFLOP/s", "frac": tfl / peak, "traffic": ncu_traffic(kernel),
            "peak_source": src, "kernel": kernel, "kernel_ms_per_step": k_ms, "flop_per_iteration": flop_iter,
            "note": "fp32-equivalent flop 4*N^2*B per update"}
-    if kernel == "batched_imma":
+    if kernel.startswith("batched_imma"):
         mt, nks = (N + 127) // 128, (N + 31) // 32
         nks = (nks + 2) // 3 * 3 if nks >= 3 else nks
-        ctas = (B + 31) // 32
-        macs = 2 * mt * nks * 128 * (96 + 64 + 32) * 32 * ctas  # per update: (matrix, M tile, K step) x three MMAs of N = 96, 64, 32
+        group = 64 if kernel.endswith("pair") else 32  # problems sharing one pass over the digit planes of Q
+        groups = (B + group - 1) // group
+        # per update and group: (matrix, M tile, K step) x three MMAs of N = 3g, 2g, g columns, M = 128, K = 32
+        macs = 2 * mt * nks * 128 * (6 * group) * 32 * groups
         tops = 2.0 * macs * iters / (k_ms * 1e-3) / 1e12
         out.update(executed_int8_tops=tops, executed_frac_of_nominal_int8=tops / 4500.0,
                    note=out["note"] + "; 6 int8 digit-plane products per fp32 product, exact int32 accumulation in TMEM")

@@ -642,8 +642,10 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			int cluster = 1;
 			if (getenv("PQP_IMMA_CLUSTER")) cluster = atoi(getenv("PQP_IMMA_CLUSTER"));
 			if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) cluster = 1;
+			/* fixed count, more than one 32-problem tile, at least two M tiles: the CTA-pair kernel (64 problems per pair, rows of Q
+			 * split over the two SMs) moves half the operand bytes per problem through shared memory */
 			const int pair = iters > 0 && B > 32 && pqp_batched_imma_pair_supported(N) &&
-					 (getenv("PQP_IMMA_PAIR") ? atoi(getenv("PQP_IMMA_PAIR")) != 0 : 0);
+					 (getenv("PQP_IMMA_PAIR") ? atoi(getenv("PQP_IMMA_PAIR")) != 0 : 1);
 			if (pair) {
 				CK(pqp_launch_batched_imma_pair(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, h->smem_optin, h->stream));
 				h->last_kernel = "batched_imma_pair";

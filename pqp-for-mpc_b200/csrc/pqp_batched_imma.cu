@@ -57,7 +57,12 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 	constexpr int EW = 4 * (NB / PW);    /* epilogue warps: 4 lane quarters x NB/PW problem groups of PW problems per thread */
 	constexpr int ETHREADS = 32 * EW;
 	constexpr uint32_t UNIT_COLS = 3 * NB;
-	constexpr uint32_t TMEM_COLS = (2 * UNIT_COLS <= 128) ? 128u : ((2 * UNIT_COLS <= 256) ? 256u : 512u);
+	/* Fd of the CTA's rows never changes: with 32 problems per CTA it fits in the TMEM columns the two accumulator buffers leave
+	 * free (column 2*UNIT_COLS + 32*mt + problem) and is read back with tcgen05.ld instead of an L2 round trip per update */
+	constexpr bool FD_TMEM = (NB == 32) && (PW == 8);
+	constexpr uint32_t FD_COL0 = 2 * UNIT_COLS;
+	constexpr uint32_t TMEM_NEED = 2 * UNIT_COLS + (FD_TMEM ? (uint32_t)(BI_MAX_MT * NB) : 0u);
+	constexpr uint32_t TMEM_COLS = TMEM_NEED <= 128 ? 128u : (TMEM_NEED <= 256 ? 256u : 512u);
 
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
@@ -317,6 +322,17 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 				y[mt][j] = v;
 			}
 		}
+		if (FD_TMEM) {
+#pragma unroll
+			for (int mt = 0; mt < BI_MAX_MT; mt++) {
+				const int i = mt * 128 + r;
+				float fv[8];
+#pragma unroll
+				for (int j = 0; j < 8; j++) fv[j] = (mt < MT && i < N && b0 + pb + j < p.B) ? __ldg(p.Fd + (size_t)(b0 + pb + j) * N + i) : 1.0f;
+				tmem_st8_f32(tmem + lane_addr + FD_COL0 + (uint32_t)(mt * NB + pb), fv);
+			}
+			umma::tc_fence_before();
+		}
 #pragma unroll
 		for (int mt = 0; mt < BI_MAX_MT; mt++)
 			if (mt < MT) publish_tile_max(y[mt], smax + NB); /* parity 1 = "planes for iteration 0" (iteration it publishes into parity it&1) */
@@ -344,8 +360,10 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 				if (mt < MT) {
 					const int i = mt * 128 + r;
 					float fd[PW];
+					if (!FD_TMEM) {
 #pragma unroll
-					for (int j = 0; j < PW; j++) fd[j] = (i < N && b0 + pb + j < p.B) ? __ldg(p.Fd + (size_t)(b0 + pb + j) * N + i) : 1.0f;
+						for (int j = 0; j < PW; j++) fd[j] = (i < N && b0 + pb + j < p.B) ? __ldg(p.Fd + (size_t)(b0 + pb + j) * N + i) : 1.0f;
+					}
 					float sn[PW];
 					float e_viol[PW], e_min[PW], e_gap[PW], e_jd[PW], e_kkt[PW]; /* evaluation pass only */
 #pragma unroll
@@ -369,6 +387,7 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 						tmem_ld_i32<PW>(col, w0);
 						tmem_ld_i32<PW>(col + NB, w1);
 						tmem_ld_i32<PW>(col + 2 * NB, w2);
+						if (FD_TMEM && mat == 0) tmem_ld8_i32(tmem + lane_addr + FD_COL0 + (uint32_t)(mt * NB + pb), reinterpret_cast<int *>(fd));
 						tmem_ld_wait();
 						umma::tc_fence_before();
 						__syncwarp();

@@ -28,11 +28,25 @@ def test_imma_is_bit_identical_to_its_model(pqp, pH, nS, nI, B, K):
     prob, d, X = _mpc(11, pH, nS, nI, B)
     with pqp.Solver(d, prob, batch_capacity=B) as s:
         Y, _, _ = s.solve(X, iters=K, status=False)
-        assert s.last_kernel == "batched_imma"
+        assert s.last_kernel in ("batched_imma", "batched_imma_pair")
         Qd, th, _ = s.dual()
         Fd, _ = s.linear_terms(B, want_fp=False)
     n = min(B, 40)
     assert np.array_equal(Y[:n], model_run(Qd, th, Fd[:n], K), equal_nan=True)
+
+
+@pytest.mark.parametrize("pH,nS,nI,B,K", [(30, 12, 4, 130, 150), (17, 4, 4, 97, 40), (9, 4, 4, 64, 30), (32, 4, 4, 33, 20)])
+def test_single_cta_and_pair_kernels_are_bit_identical(pqp, monkeypatch, pH, nS, nI, B, K):
+    """The CTA-pair kernel (two SMs share 64 problems, each multiplies half the M tiles, digit planes exchanged through DSMEM)
+    and the single-CTA kernel run the same arithmetic: same bits, for 2, 3 and 4 M tiles and ragged batches."""
+    prob, d, X = _mpc(7, pH, nS, nI, B)
+    out = {}
+    for pair in ("0", "1"):
+        monkeypatch.setenv("PQP_IMMA_PAIR", pair)
+        with pqp.Solver(d, prob, batch_capacity=B) as s:
+            out[pair], _, _ = s.solve(X, iters=K, status=False)
+            assert s.last_kernel == ("batched_imma_pair" if pair == "1" else "batched_imma")
+    assert np.array_equal(out["0"], out["1"], equal_nan=True)
 
 
 def test_imma_warm_start_and_chunking_are_exact(pqp):
@@ -57,7 +71,7 @@ def test_c4_shape_against_oracle(pqp, oracle32, oracle64):
     K = 1000
     with pqp.Solver(d, prob, batch_capacity=200) as s:
         Y, U, st = s.solve(X, iters=K, primal=True)
-        assert s.last_kernel == "batched_imma"
+        assert s.last_kernel == "batched_imma_pair"
         Qd, th, _ = s.dual()
         Fd, Fp = s.linear_terms(200)
     worst = 0.0
@@ -82,7 +96,7 @@ def test_c4_full_size_properties(pqp, oracle32):
     prob, d, X = _mpc(2024, 30, 12, 4, 4096)
     with pqp.Solver(d, prob, batch_capacity=4096) as s:
         Y, U, st = s.solve(X, iters=1000, primal=True)
-        assert s.last_kernel == "batched_imma"
+        assert s.last_kernel == "batched_imma_pair"
         Fd, _ = s.linear_terms(4096, want_fp=False)
         Qd, _, _ = s.dual()
         Y2, _, st2 = s.solve(X, iters=1500)
@@ -109,7 +123,7 @@ def test_engines_agree_within_tolerance(pqp, oracle32, oracle64):
     for name, tc in (("imma", 1), ("simt", 0), ("umma", 2)):
         with pqp.Solver(d, prob, batch_capacity=64, use_tensor_cores=tc) as s:
             out[name], _, _ = s.solve(X, iters=K, status=False)
-            assert s.last_kernel == "batched_" + name
+            assert s.last_kernel.startswith("batched_" + name)
             Qd, th, _ = s.dual()
             Fd, _ = s.linear_terms(64, want_fp=False)
     for b in (0, 31, 63):
