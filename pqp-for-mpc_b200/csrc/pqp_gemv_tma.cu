@@ -277,38 +277,99 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 			if (tid < nrows) y_mine = __ldcg(y_in + r0 + tid);
 		}
 
-		for (int t = 0; t < nrows; t++) {
-			const float4 *src;
-			int s = 0;
-			if (t < R) {
-				src = reinterpret_cast<const float4 *>(resid + (size_t)t * ldq);
-			} else {
-				s = (int)(idx % S);
-				mbar_wait(&full[s], (uint32_t)((idx / S) & 1));
-				src = reinterpret_cast<const float4 *>(ring + (size_t)s * ldq);
-			}
-			float num = 0.0f, den = 0.0f;
-			float4 q[YC];
-#pragma unroll
-			for (int u = 0; u < YC; u++) {
-				const int c = tid + u * CONSUMERS;
-				q[u] = (c < n4) ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-			}
-			if (t >= R) {
+		if constexpr (YC <= 2) { /* short rows (N <= 4096): the loop is issue-bound, not bandwidth-bound (ncu: L2 hit 99 %, issue slots 53 %) */
+			/*
+			 * Rows are taken two at a time: both rows' operands are in registers before the arithmetic starts (twice the independent
+			 * work per wait), and the two xor-shuffle trees are folded into one -- after the first exchange (xor 16) lanes 0-15 carry
+			 * row t and lanes 16-31 row t+1, so the remaining four steps serve both rows.  The pairing of partial sums is exactly that
+			 * of the one-row tree (16, 8, 4, 2, 1), hence the same bits as pqp_gemv.cu.
+			 */
+			for (int t = 0; t < nrows; t += 2) {
+				const bool two = (t + 1 < nrows);
+				const float4 *src[2];
+				int sidx[2] = { 0, 0 };
+	#pragma unroll
+				for (int k = 0; k < 2; k++) {
+					const int tt = t + k;
+					if (k == 1 && !two) {
+						src[k] = src[0];
+					} else if (tt < R) {
+						src[k] = reinterpret_cast<const float4 *>(resid + (size_t)tt * ldq);
+					} else {
+						sidx[k] = (int)(idx % S);
+						mbar_wait(&full[sidx[k]], (uint32_t)((idx / S) & 1));
+						src[k] = reinterpret_cast<const float4 *>(ring + (size_t)sidx[k] * ldq);
+						idx++;
+					}
+				}
+				float4 q0[YC], q1[YC];
+	#pragma unroll
+				for (int u = 0; u < YC; u++) {
+					const int c = tid + u * CONSUMERS;
+					q0[u] = (c < n4) ? src[0][c] : make_float4(0.f, 0.f, 0.f, 0.f);
+					q1[u] = (two && c < n4) ? src[1][c] : make_float4(0.f, 0.f, 0.f, 0.f);
+				}
 				__syncwarp();
-				if (lane == 0) mbar_arrive(&empty[s]); /* the row is in registers: hand the stage back */
-				idx++;
+				if (lane == 0) { /* the rows are in registers: hand the stages back */
+					if (t >= R) mbar_arrive(&empty[sidx[0]]);
+					if (two && t + 1 >= R) mbar_arrive(&empty[sidx[1]]);
+				}
+				float num0 = 0.0f, den0 = 0.0f, num1 = 0.0f, den1 = 0.0f;
+	#pragma unroll
+				for (int u = 0; u < YC; u++) {
+					acc4t(num0, den0, q0[u], yv[u]);
+					acc4t(num1, den1, q1[u], yv[u]);
+				}
+				/* xor 16: lower half keeps row t, upper half row t+1 */
+				const bool up = lane >= 16;
+				const float sn = up ? num0 : num1, sd = up ? den0 : den1; /* what this lane gives away */
+				const float rn = __shfl_xor_sync(0xffffffffu, sn, 16), rd = __shfl_xor_sync(0xffffffffu, sd, 16);
+				float num = (up ? num1 : num0) + rn, den = (up ? den1 : den0) + rd;
+	#pragma unroll
+				for (int o = 8; o; o >>= 1) {
+					num += __shfl_xor_sync(0xffffffffu, num, o);
+					den += __shfl_xor_sync(0xffffffffu, den, o);
+				}
+				if ((lane & 15) == 0 && (!up || two)) {
+					const int tt = t + (up ? 1 : 0);
+					part[(0 * PQP_GEMV_WARPS + warp) * rows_max + tt] = num;
+					part[(1 * PQP_GEMV_WARPS + warp) * rows_max + tt] = den;
+				}
 			}
-#pragma unroll
-			for (int u = 0; u < YC; u++) acc4t(num, den, q[u], yv[u]);
-#pragma unroll
-			for (int o = 16; o; o >>= 1) {
-				num += __shfl_xor_sync(0xffffffffu, num, o);
-				den += __shfl_xor_sync(0xffffffffu, den, o);
-			}
-			if (lane == 0) {
-				part[(0 * PQP_GEMV_WARPS + warp) * rows_max + t] = num;
-				part[(1 * PQP_GEMV_WARPS + warp) * rows_max + t] = den;
+		} else { /* long rows: one row per step (two would need two 32-48 KB stages at once and 2*YC float4 of operands in registers) */
+			for (int t = 0; t < nrows; t++) {
+				const float4 *src;
+				int s = 0;
+				if (t < R) {
+					src = reinterpret_cast<const float4 *>(resid + (size_t)t * ldq);
+				} else {
+					s = (int)(idx % S);
+					mbar_wait(&full[s], (uint32_t)((idx / S) & 1));
+					src = reinterpret_cast<const float4 *>(ring + (size_t)s * ldq);
+				}
+				float num = 0.0f, den = 0.0f;
+				float4 q[YC];
+	#pragma unroll
+				for (int u = 0; u < YC; u++) {
+					const int c = tid + u * CONSUMERS;
+					q[u] = (c < n4) ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+				}
+				if (t >= R) {
+					__syncwarp();
+					if (lane == 0) mbar_arrive(&empty[s]); /* the row is in registers: hand the stage back */
+					idx++;
+				}
+	#pragma unroll
+				for (int u = 0; u < YC; u++) acc4t(num, den, q[u], yv[u]);
+	#pragma unroll
+				for (int o = 16; o; o >>= 1) {
+					num += __shfl_xor_sync(0xffffffffu, num, o);
+					den += __shfl_xor_sync(0xffffffffu, den, o);
+				}
+				if (lane == 0) {
+					part[(0 * PQP_GEMV_WARPS + warp) * rows_max + t] = num;
+					part[(1 * PQP_GEMV_WARPS + warp) * rows_max + t] = den;
+				}
 			}
 		}
 		consumer_sync();
