@@ -22,8 +22,9 @@ import numpy as np
 
 
 def condensed_mpc(seed: int, pH: int = 30, nS: int = 12, nI: int = 4, n_states: int = 4096, x_scale: float = 60.0,
-                  umax: float = 20.0, ymax: float = 30.0):
-    """Returns (problem dict for pqp.Solver, pqp Dims, X [n_states x nS] float32)."""
+                  umax: float = 20.0, ymax: float = 30.0, return_plant: bool = False):
+    """Returns (problem dict for pqp.Solver, pqp Dims, X [n_states x nS] float32) and, with return_plant, the plant
+    (A, B, E) the condensed matrices were built from (for closed-loop drivers: x+ = A x + B u + E d)."""
     import pqp_for_mpc_b200 as pqp
 
     rng = np.random.default_rng(seed)
@@ -71,6 +72,8 @@ def condensed_mpc(seed: int, pH: int = 30, nS: int = 12, nI: int = 4, n_states: 
     d = pqp.dims_mpc(pH, nS, nI, nI, 1)
     X = f32(rng.standard_normal((n_states, nS)) * x_scale)
     prob["x"] = X[0].copy()
+    if return_plant:
+        return prob, d, X, (f32(A), f32(Bm), f32(E))
     return prob, d, X
 
 

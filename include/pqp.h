@@ -192,6 +192,17 @@ int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B,
 			   float *Y, float *U, pqp_status *st);
 
 /*
+ * Receding-horizon warm start (the caller the report describes, PQP_CPU.c:710 always restarts from 1000).
+ * The duals of a condensed MPC QP come in four blocks of pHorizon*nInput rows (N = 4*pHorizon*nInput, PQP_CPU.c:941), each
+ * ordered by horizon step: Ynext[blk][k] = max(Y[blk][k+1], y_floor) for k < pHorizon-1, and the last step is held.  The floor
+ * matters: the multiplicative update can never leave y_i = 0, so a dual that went to zero while its constraint was inactive
+ * could not become active again in a later period (the reference avoids the question by restarting from 1000 every time).
+ * Y, Ynext [B x N], host or device; Ynext may equal Y.  Feed Ynext as Y0 to the next period's pqp_solve_batch.  Needs
+ * dims.pHorizon*nInput*4 == N.  Uses the handle's workspace (call pqp_get_linear_terms before it, not after).
+ */
+int pqp_shift_duals(pqp_handle *h, const float *Y, int B, float y_floor, float *Ynext);
+
+/*
  * out[a x c] = op(A)[a x b] * op(B)[b x c] on the GPU: the reference's matrixMultiply (PQP_CPU.c:84-147) with its
  * transpose flags (tA: A is stored [b x a]; tB: B is stored [c x b]).  engine: PQP_MM_STRICT = the reference's
  * summation order, bit-identical; PQP_MM_SIMT = fp32 FMA tiles; PQP_MM_TENSOR = tcgen05 3xTF32 (fp32-level accuracy).

@@ -69,7 +69,7 @@ ABI_SYMBOLS = (
     "pqp_load_example", "pqp_load_testfile", "pqp_generate_testproblem", "pqp_write_testfile", "pqp_free_problem",
     "pqp_setup", "pqp_setup_dual", "pqp_destroy", "pqp_solve_batch", "pqp_solve_dual", "pqp_recover_primal",
     "pqp_solve_batch_primal", "pqp_get_dual", "pqp_get_linear_terms", "pqp_get_stream", "pqp_last_solve_ms",
-    "pqp_launch_count", "pqp_last_kernel", "pqp_device_qd", "pqp_matmul",
+    "pqp_launch_count", "pqp_last_kernel", "pqp_device_qd", "pqp_matmul", "pqp_shift_duals",
 )
 MM_STRICT, MM_SIMT, MM_TENSOR = 0, 1, 2
 
@@ -321,6 +321,16 @@ class Solver:
         if rc:
             raise PQPError(rc, where)
         return Y, U, st
+
+    def shift_duals(self, Y, y_floor=0.0):
+        """pqp_shift_duals: the receding-horizon warm start for the next control period (each of the four constraint blocks
+        moves one horizon step forward, the last step is held, values below y_floor are raised to it)."""
+        Y = np.ascontiguousarray(Y, np.float32).reshape(-1, self.dims.N)
+        out = np.empty_like(Y)
+        rc = lib().pqp_shift_duals(self._h, _as_ptr(Y), Y.shape[0], C.c_float(y_floor), _as_ptr(out))
+        if rc:
+            raise PQPError(rc, "pqp_shift_duals")
+        return out
 
     def recover(self, Y, Fp=None):
         """pqp_recover_primal: U = -Qp_inv (Gp' Y + Fp)  (computeUfromY, PQP_CPU.c:352)."""

@@ -799,6 +799,26 @@ int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B,
 	return PQP_OK;
 }
 
+/* ---- receding-horizon warm start -------------------------------------------------------------- */
+int pqp_shift_duals(pqp_handle *h, const float *Y, int B, float y_floor, float *Ynext)
+{
+	if (!h || !Y || !Ynext || B <= 0) return PQP_ERR_INVALID;
+	const int N = h->d.N, pH = h->d.pHorizon, nI = h->d.nInput;
+	if (pH <= 0 || nI <= 0 || 4 * pH * nI != N) return PQP_ERR_INVALID; /* not an MPC-structured dual */
+	CK(cudaSetDevice(h->device));
+	if (B > h->cap) {
+		int rc = ensure_capacity(h, B);
+		if (rc) return rc;
+	}
+	/* staged through the workspace: h->Fd is rewritten by every solve, so it is free between solves */
+	CK(cudaMemcpyAsync(h->Fd, Y, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+	CK(pqp_launch_shift_duals(h->Y, h->Fd, B, pH, nI, y_floor, h->stream));
+	h->launches++;
+	CK(cudaMemcpyAsync(Ynext, h->Y, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	return PQP_OK;
+}
+
 /* ---- matrixMultiply (PQP_CPU.c:84-147) on the device ---------------------------------------- */
 int pqp_matmul(float *out, const float *A, int tA, const float *B, int tB, int a, int b, int c, int engine, int device)
 {

@@ -48,6 +48,8 @@ cudaError_t pqp_launch_md(float *Md, const float *Fp, const float *Qp_inv, const
 /* U[b] = -(Qp_inv*(Gp'*Y[b] + Fp[b])) (computeUfromY, PQP_CPU.c:352-360); tmp [B x M] scratch */
 cudaError_t pqp_launch_recover(float *U, float *tmp, const float *Y, int ldy, const float *Fp, const float *Gp,
 			       const float *Qp_inv, int B, int N, int M, int strict, cudaStream_t s);
+/* receding-horizon shift of the duals (out must not alias in) */
+cudaError_t pqp_launch_shift_duals(float *out, const float *in, int B, int pH, int nI, float y_floor, cudaStream_t s);
 /* fill n floats */
 cudaError_t pqp_launch_fill(float *p, float v, size_t n, cudaStream_t s);
 

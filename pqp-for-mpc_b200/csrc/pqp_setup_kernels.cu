@@ -432,3 +432,26 @@ cudaError_t pqp_launch_status(pqp_status *st, const float *Q, int ldq, int N, co
 	status_kernel<<<B, 256, 0, s>>>(st, Q, ldq, N, Y, ldy, Fd, Md, Kp, erc, eac, iters);
 	return cudaGetLastError();
 }
+
+/* receding-horizon shift of the duals: four blocks of pH steps x nI rows; step k takes step k+1, the last step is held */
+__global__ void shift_duals_kernel(float *__restrict__ out, const float *__restrict__ in, int B, int pH, int nI, float y_floor)
+{
+	const int N = 4 * pH * nI;
+	const size_t total = (size_t)B * N;
+	for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+		const int i = (int)(e % N);
+		const int blk = i / (pH * nI), within = i % (pH * nI), k = within / nI, j = within % nI;
+		const int ks = k + 1 < pH ? k + 1 : k;
+		out[e] = fmaxf(in[e - i + (size_t)blk * pH * nI + (size_t)ks * nI + j], y_floor);
+	}
+}
+
+cudaError_t pqp_launch_shift_duals(float *out, const float *in, int B, int pH, int nI, float y_floor, cudaStream_t s)
+{
+	const size_t total = (size_t)B * 4 * pH * nI;
+	size_t blocks = (total + 255) / 256;
+	if (blocks > 148 * 8) blocks = 148 * 8;
+	if (blocks < 1) blocks = 1;
+	shift_duals_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, in, B, pH, nI, y_floor);
+	return cudaGetLastError();
+}

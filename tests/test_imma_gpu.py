@@ -170,3 +170,34 @@ def test_batched_run_to_tolerance_retires_degenerate_states(pqp):
         good = ~nan_states
         assert st["converged"][good].mean() > 0.9
         assert np.median(st["iters"][good]) < 3000
+
+
+def test_receding_horizon_warm_start(pqp, oracle32):
+    """the MPC loop the report describes.  pqp_shift_duals moves each of the four constraint blocks one horizon
+    step forward; warm-started periods reach the same controls as cold-started ones in fewer updates; the first period equals
+    the plain solve; and the shift itself is checked against numpy."""
+    sys_path_tools = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    import sys
+    sys.path.insert(0, sys_path_tools)
+    from mpc_closed_loop import closed_loop
+    from bench_problems import condensed_mpc
+    pH, nS, nI, B, T = 8, 4, 3, 64, 5
+    prob, d, X, plant = condensed_mpc(5, pH, nS, nI, n_states=B, x_scale=20.0, return_plant=True)
+    opts = dict(batch_capacity=B, eaj=1e-3, erj=1e-6, check_every=8, max_iters=20000)
+    with pqp.Solver(d, prob, **opts) as s:
+        Y, _, _ = s.solve(X, iters=50)
+        Ys = s.shift_duals(Y, 0.25)
+        ref = Y.reshape(B, 4, pH, nI).copy()
+        ref[:, :, :-1] = ref[:, :, 1:]
+        assert np.array_equal(Ys, np.maximum(ref.reshape(B, -1), np.float32(0.25)))
+        Xc, Uc, stc = closed_loop(s, plant, d, prob, X, T, warm=False)
+        Xw, Uw, stw = closed_loop(s, plant, d, prob, X, T, warm=True)
+    ok = np.logical_and.reduce([st["converged"] == 1 for st in stc + stw])
+    assert ok.mean() >= 0.9, ok.mean()
+    assert np.array_equal(Uc[0], Uw[0])                                # the first period has nothing to warm-start from
+    scale = np.abs(Uc[:, ok]).max()
+    assert np.abs(Uc[:, ok] - Uw[:, ok]).max() <= 5e-3 * scale         # same controls up to the stop tolerance
+    its_c = sum(int(st["iters"][ok].sum()) for st in stc[1:])
+    its_w = sum(int(st["iters"][ok].sum()) for st in stw[1:])
+    assert its_w < 0.8 * its_c, (its_w, its_c)
+    assert np.abs(Xw[-1][ok]).mean() < np.abs(Xw[0][ok]).mean()        # the loop regulates
