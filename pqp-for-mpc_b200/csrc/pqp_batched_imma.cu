@@ -240,16 +240,9 @@ __global__ void __launch_bounds__(64 + 128 * (NB / PW), 1) batched_imma_kernel(c
 			if (i < Kpad) {
 				uint32_t w0[4] = { 0, 0, 0, 0 }, w1[4] = { 0, 0, 0, 0 }, w2[4] = { 0, 0, 0, 0 };
 #pragma unroll
-				for (int j = 0; j < PW; j++) {
-					const int b = __float2int_rn(yv[j] * sc[j]);
-					const int d2 = (int)(signed char)b;
-					const int b1 = (b - d2) >> 8;
-					const int d1 = (int)(signed char)b1;
-					const int d0 = (b1 - d1) >> 8;
-					w0[j >> 2] |= ((uint32_t)d0 & 255u) << (8 * (j & 3));
-					w1[j >> 2] |= ((uint32_t)d1 & 255u) << (8 * (j & 3));
-					w2[j >> 2] |= ((uint32_t)d2 & 255u) << (8 * (j & 3));
-				}
+				for (int j = 0; j < PW; j += 4)
+					digits4(__float2int_rn(yv[j] * sc[j]), __float2int_rn(yv[j + 1] * sc[j + 1]), __float2int_rn(yv[j + 2] * sc[j + 2]),
+						__float2int_rn(yv[j + 3] * sc[j + 3]), w0[j >> 2], w1[j >> 2], w2[j >> 2]);
 				unsigned char *dst = Bpl + buf * pbuf_bytes + (uint32_t)(pb >> 4) * p.b_sbo + (uint32_t)(i >> 3) * BI_B_LBO + (uint32_t)(i & 7) * 16u +
 						     (uint32_t)(pb & 15);
 				if (PW == 16) {

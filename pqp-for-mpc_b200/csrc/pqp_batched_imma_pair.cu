@@ -56,6 +56,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr)
 {
 	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
 }
+/* relaxed arrival; the caller has issued fence_release_cluster() after its writes */
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t addr)
+{
+	asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void fence_release_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
 {
 	asm volatile(
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1) batched_imma_pair_kernel(const 
 	const int chunks_per_unit = NKS / p.ksc;
 	const int b0 = (int)(blockIdx.x / 2) * NB;
 	const bool prof_on = (p.dbg & 8) && p.prof && blockIdx.x == 0;
-	long long prof_acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	long long prof_acc[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 
 	if (tid == 0) {
 		for (int s = 0; s < p.stages; s++) {
@@ -233,11 +239,15 @@ __global__ void __launch_bounds__(BP_THREADS, 1) batched_imma_pair_kernel(const 
 		/* exchange: exact maxima -> scales -> digits of the own rows into both plane buffers */
 		auto exchange = [&](int parity, uint32_t phase) {
 			__syncwarp(); /* every lane's max publications precede lane 0's (release) arrivals */
-			if (lane == 0) {
-				mbar_arrive_cluster(allmax_l);
-				mbar_arrive_cluster(allmax_r);
+			if (lane == 0) { /* one release fence for both arrivals */
+				fence_release_cluster();
+				mbar_arrive_cluster_relaxed(allmax_l);
+				mbar_arrive_cluster_relaxed(allmax_r);
 			}
+			PROF_T(tx0);
 			mbar_wait_cluster(allmax, phase);
+			PROF_ADD(8, tx0);
+			PROF_T(tx1);
 			float sc[PW];
 #pragma unroll
 			for (int j = 0; j < PW; j++) {
@@ -254,18 +264,11 @@ __global__ void __launch_bounds__(BP_THREADS, 1) batched_imma_pair_kernel(const 
 			for (int lt = 0; lt < BP_MAX_MY; lt++) {
 				const int i = ((int)rank + 2 * lt) * 128 + r;
 				if (lt < n_my && i < Kpad) {
-					uint32_t w0[4] = { 0, 0, 0, 0 }, w1[4] = { 0, 0, 0, 0 }, w2[4] = { 0, 0, 0, 0 };
+					uint32_t w0[4], w1[4], w2[4];
 #pragma unroll
-					for (int j = 0; j < PW; j++) {
-						const int b = __float2int_rn(y[lt][j] * sc[j]);
-						const int d2 = (int)(signed char)b;
-						const int b1 = (b - d2) >> 8;
-						const int d1 = (int)(signed char)b1;
-						const int d0 = (b1 - d1) >> 8;
-						w0[j >> 2] |= ((uint32_t)d0 & 255u) << (8 * (j & 3));
-						w1[j >> 2] |= ((uint32_t)d1 & 255u) << (8 * (j & 3));
-						w2[j >> 2] |= ((uint32_t)d2 & 255u) << (8 * (j & 3));
-					}
+					for (int j = 0; j < PW; j += 4)
+						digits4(__float2int_rn(y[lt][j] * sc[j]), __float2int_rn(y[lt][j + 1] * sc[j + 1]),
+							__float2int_rn(y[lt][j + 2] * sc[j + 2]), __float2int_rn(y[lt][j + 3] * sc[j + 3]), w0[j >> 2], w1[j >> 2], w2[j >> 2]);
 					const uint32_t off = (uint32_t)cg * p.b_sbo + (uint32_t)(i >> 3) * BI_B_LBO + (uint32_t)(i & 7) * 16u;
 					const uint4 v0 = make_uint4(w0[0], w0[1], w0[2], w0[3]), v1 = make_uint4(w1[0], w1[1], w1[2], w1[3]),
 						    v2 = make_uint4(w2[0], w2[1], w2[2], w2[3]);
@@ -277,11 +280,15 @@ __global__ void __launch_bounds__(BP_THREADS, 1) batched_imma_pair_kernel(const 
 					st_cluster_v4(planes_r + off + 2u * plane_bytes, v2);
 				}
 			}
+			PROF_ADD(9, tx1);
+			PROF_T(tx2);
 			fence_proxy_async_all(); /* local and remote digits must be visible to both tensor cores */
+			PROF_ADD(10, tx2);
 			__syncwarp();
 			if (lane == 0) {
-				mbar_arrive_cluster(bready_l);
-				mbar_arrive_cluster(bready_r);
+				fence_release_cluster();
+				mbar_arrive_cluster_relaxed(bready_l);
+				mbar_arrive_cluster_relaxed(bready_r);
 			}
 		};
 
@@ -378,8 +385,10 @@ __global__ void __launch_bounds__(BP_THREADS, 1) batched_imma_pair_kernel(const 
 			PROF_ADD(PROF_EPI_REQUANT, tq);
 		}
 		PROF_ADD(PROF_EPI_TOTAL, te0);
-		if (prof_on && et == 0)
+		if (prof_on && et == 0) {
 			for (int i = PROF_EPI_TOTAL; i <= PROF_EPI_REQUANT; i++) p.prof[i] = prof_acc[i];
+			for (int i = 8; i < 12; i++) p.prof[i] = prof_acc[i];
+		}
 #pragma unroll
 		for (int lt = 0; lt < BP_MAX_MY; lt++) {
 			const int i = ((int)rank + 2 * lt) * 128 + r;
@@ -432,8 +441,8 @@ cudaError_t pqp_launch_batched_imma_pair(const void *tiles, const void *rowc, in
 
 	static long long *prof_dev = NULL;
 	if (p.dbg & 8) {
-		if (!prof_dev) cudaMalloc((void **)&prof_dev, 8 * sizeof(long long));
-		cudaMemsetAsync(prof_dev, 0, 8 * sizeof(long long), s);
+		if (!prof_dev) cudaMalloc((void **)&prof_dev, 12 * sizeof(long long));
+		cudaMemsetAsync(prof_dev, 0, 12 * sizeof(long long), s);
 		p.prof = prof_dev;
 	}
 	cudaLaunchConfig_t cfg;
@@ -451,10 +460,11 @@ cudaError_t pqp_launch_batched_imma_pair(const void *tiles, const void *rowc, in
 	cfg.numAttrs = 1;
 	e = cudaLaunchKernelEx(&cfg, batched_imma_pair_kernel, p);
 	if ((p.dbg & 8) && e == cudaSuccess) {
-		long long h[8];
+		long long h[12];
 		cudaStreamSynchronize(s);
 		cudaMemcpy(h, prof_dev, sizeof h, cudaMemcpyDeviceToHost);
 		const double it = (double)iters;
+		fprintf(stderr, "  exchange split: wait allmax %.0f, scales+quantise+stores %.0f, proxy fence %.0f\n", h[8] / it, h[9] / it, h[10] / it);
 		fprintf(stderr,
 			"imma pair profile (CTA 0, cycles per update): mma warp total %.0f = wait b_ready %.0f + wait tmem_empty %.0f + wait full(stream) %.0f + issue %.0f | "
 			"epilogue total %.0f = wait tmem_full %.0f + exchange %.0f + drain/math %.0f | producer wait empty %.0f\n",

@@ -203,6 +203,22 @@ __device__ __forceinline__ void problem_scales(uint32_t pmax_bits, float &sc, fl
 	isc = __uint_as_float((ex - 21u) << 23);  /* 2^(ex-148) */
 }
 
+/*
+ * Signed base-256 digits of four quantised duals b0..b3 (0 <= b <= 2^22 + headroom), packed one plane per word:
+ *   b = Y0*65536 + Y1*256 + Y2,  Y1, Y2 in [-128, 127].  With c = b + 128 and c1 = (c >> 8) + 128:
+ *   Y2 = (c & 255) - 128, Y1 = (c1 & 255) - 128, Y0 = c1 >> 8; as bytes x - 128 == x ^ 0x80, applied to the packed word.
+ */
+__device__ __forceinline__ void digits4(int b0, int b1, int b2, int b3, uint32_t &w0, uint32_t &w1, uint32_t &w2)
+{
+	const uint32_t c_0 = (uint32_t)(b0 + 128), c_1 = (uint32_t)(b1 + 128), c_2 = (uint32_t)(b2 + 128), c_3 = (uint32_t)(b3 + 128);
+	const uint32_t d_0 = (uint32_t)(((int)c_0 >> 8) + 128), d_1 = (uint32_t)(((int)c_1 >> 8) + 128), d_2 = (uint32_t)(((int)c_2 >> 8) + 128),
+		       d_3 = (uint32_t)(((int)c_3 >> 8) + 128);
+	/* byte 0 of four words -> one word; byte 1 of four words -> one word */
+	w2 = __byte_perm(__byte_perm(c_0, c_1, 0x0040), __byte_perm(c_2, c_3, 0x0040), 0x5410) ^ 0x80808080u;
+	w1 = __byte_perm(__byte_perm(d_0, d_1, 0x0040), __byte_perm(d_2, d_3, 0x0040), 0x5410) ^ 0x80808080u;
+	w0 = __byte_perm(__byte_perm(d_0, d_1, 0x0051), __byte_perm(d_2, d_3, 0x0051), 0x5410);
+}
+
 } /* namespace */
 
 struct BiParams {
