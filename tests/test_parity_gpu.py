@@ -289,3 +289,20 @@ def test_c3_large_fast_vs_strict_and_kkt(pqp, oracle32, oracle64):
         Y2, _, st2 = s.solve(iters=600)
         assert st2["kkt"][0] <= st["kkt"][0] * 1.001
         assert st2["iters"][0] == 600
+
+
+def test_reference_main_flow_through_the_compat_library(pqp, gold_example):
+    """PQP_CPU.c's main() sequence, written against the reference's own function names
+    (convertToDual, solveQuadraticDual, computeUfromY, computeFp, computeCost from libpqp_compat.so), prints exactly what the
+    reference prints for example/ -- iterations, Jp, Jd and U* to the last digit (STRICT order, 312 updates)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pqp.LIB_PATH), "pqp_example.bin")
+    assert os.path.exists(exe), "pqp_example.bin not built (make -C pqp-for-mpc_b200/csrc)"
+    out = subprocess.run([exe, EXAMPLE_DIR], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.strip() == str(gold_example["stdout"]).strip()
+    fast = subprocess.run([exe, EXAMPLE_DIR, "--fast"], capture_output=True, text=True, timeout=120)
+    assert fast.returncode == 0, fast.stderr
+    ref_u = [float(t) for t in str(gold_example["stdout"]).split("Printing U*")[1].split()]
+    got_u = [float(t) for t in fast.stdout.split("Printing U*")[1].split()]
+    assert np.allclose(got_u, ref_u, atol=2e-5)
