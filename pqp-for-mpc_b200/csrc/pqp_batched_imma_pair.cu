@@ -275,9 +275,11 @@ __global__ void __launch_bounds__(BP_THREADS, 1) batched_imma_pair_kernel(const 
 					*reinterpret_cast<uint4 *>(Bpl + off) = v0;
 					*reinterpret_cast<uint4 *>(Bpl + off + plane_bytes) = v1;
 					*reinterpret_cast<uint4 *>(Bpl + off + 2u * plane_bytes) = v2;
-					st_cluster_v4(planes_r + off, v0);
-					st_cluster_v4(planes_r + off + plane_bytes, v1);
-					st_cluster_v4(planes_r + off + 2u * plane_bytes, v2);
+					if (!(p.dbg & 16)) { /* experiment switch: timing without the remote stores (results are then wrong) */
+						st_cluster_v4(planes_r + off, v0);
+						st_cluster_v4(planes_r + off + plane_bytes, v1);
+						st_cluster_v4(planes_r + off + 2u * plane_bytes, v2);
+					}
 				}
 			}
 			PROF_ADD(9, tx1);
