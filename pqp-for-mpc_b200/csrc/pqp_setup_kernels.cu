@@ -227,17 +227,47 @@ cudaError_t pqp_launch_fp(float *Fp, const float *Fp1, const float *Fp2, const f
 	return cudaGetLastError();
 }
 
-/* Fd = GQ*Fp + Kp.  Thread per (problem, row), k ascending: the reference's order (PQP_CPU.c:458-459). */
-__global__ void fd_seq_kernel(float *__restrict__ Fd, const float *__restrict__ GQ, const float *__restrict__ Fp,
-			      const float *__restrict__ Kp, int B, int N, int M)
+/*
+ * Fd = GQ*Fp + Kp.  One output per thread, k ascending, separately rounded mul and add: the reference's order
+ * (PQP_CPU.c:458-459), so Fd is bit-identical to the oracle's in every mode.  A block forms a 32-row x 32-problem tile of
+ * outputs from shared-memory copies of the two operand tiles (coalesced loads; the k loop then reads a broadcast GQ value and a
+ * conflict-free Fp column), instead of every thread walking its own strided row of GQ in global memory.
+ */
+#define FD_TR 32
+#define FD_TB 32
+#define FD_KC 64
+__global__ void __launch_bounds__(FD_TR * FD_TB / 4)
+fd_seq_kernel(float *__restrict__ Fd, const float *__restrict__ GQ, const float *__restrict__ Fp, const float *__restrict__ Kp, int B, int N,
+	      int M)
 {
-	const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= (long long)B * N) return;
-	const int b = (int)(t / N), i = (int)(t % N);
-	const float *g = GQ + (size_t)i * M, *f = Fp + (size_t)b * M;
-	float acc = 0.0f;
-	for (int k = 0; k < M; k++) acc = __fadd_rn(acc, __fmul_rn(g[k], f[k]));
-	Fd[t] = __fadd_rn(acc, __fmul_rn(1.0f, Kp[i]));
+	__shared__ float g_s[FD_TR][FD_KC + 1], f_s[FD_TB][FD_KC + 1];
+	const int i0 = blockIdx.x * FD_TR, b0 = blockIdx.y * FD_TB;
+	const int tid = threadIdx.x;          /* 256 threads: thread = (row r, problem group of 4) */
+	const int r = tid % FD_TR, pg = tid / FD_TR; /* pg in 0..7 -> problems pg, pg+8, pg+16, pg+24 */
+	float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+	for (int k0 = 0; k0 < M; k0 += FD_KC) {
+		const int kc = min(FD_KC, M - k0);
+		for (int e = tid; e < FD_TR * FD_KC; e += blockDim.x) {
+			const int rr = e / FD_KC, kk = e % FD_KC;
+			g_s[rr][kk] = (i0 + rr < N && kk < kc) ? GQ[(size_t)(i0 + rr) * M + k0 + kk] : 0.0f;
+			f_s[rr][kk] = (b0 + rr < B && kk < kc) ? Fp[(size_t)(b0 + rr) * M + k0 + kk] : 0.0f;
+		}
+		__syncthreads();
+		for (int k = 0; k < kc; k++) {
+			const float g = g_s[r][k];
+#pragma unroll
+			for (int u = 0; u < 4; u++) acc[u] = __fadd_rn(acc[u], __fmul_rn(g, f_s[pg + 8 * u][k]));
+		}
+		__syncthreads();
+	}
+	if (i0 + r < N) {
+		const float kp = __fmul_rn(1.0f, Kp[i0 + r]);
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const int b = b0 + pg + 8 * u;
+			if (b < B) Fd[(size_t)b * N + i0 + r] = __fadd_rn(acc[u], kp);
+		}
+	}
 }
 
 /* single problem, FAST: warp per row, coalesced, shuffle tree */
@@ -260,8 +290,7 @@ cudaError_t pqp_launch_fd(float *Fd, const float *GQ, const float *Fp, const flo
 	if (!strict && B == 1 && M >= 256) {
 		fd_warp_kernel<<<(N + 7) / 8, 256, 0, s>>>(Fd, GQ, Fp, Kp, N, M);
 	} else {
-		const long long n = (long long)B * N;
-		fd_seq_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(Fd, GQ, Fp, Kp, B, N, M);
+		fd_seq_kernel<<<dim3((N + FD_TR - 1) / FD_TR, (B + FD_TB - 1) / FD_TB), FD_TR * FD_TB / 4, 0, s>>>(Fd, GQ, Fp, Kp, B, N, M);
 	}
 	return cudaGetLastError();
 }
