@@ -16,10 +16,12 @@ The c3 line also carries the c4 numbers under "batched" so one default run repor
 
 value    whole-job throughput with inputs resident in HBM (PQP iterations/s for c2/c3, QP solves/s for c4).
 e2e      the same through the C ABI with host buffers: pinned-host Fd/X -> device, solve, Y/U -> host, every step.
-roofline algorithmic bytes (4*N*ldq + 16*N per iteration) / the iteration kernel's own CUDA-event time (recorded by
-         the library on its stream), against MEASURED_PEAKS.json.
-cpu_baseline / --impl reference: the reference's own CPU code (oracle/_ref = PQP_CPU.c compiled where it lay) or,
-         if that library did not travel, the oracle port; on a bounded sample; 1 thread (the reference has none).
+roofline algorithmic bytes (4*N*ldq + 16*N per iteration; c4: 4*N^2*B flop per update) / the iteration kernel's own
+         CUDA-event time (recorded by the library on its stream), against MEASURED_PEAKS.json (hbm_gbs; c4: the sustained
+         dense-bf16 figure, the only measured tensor number); traffic = DRAM bytes per launch from the committed ncu capture.
+cpu_baseline: the reference's own CPU code (oracle/_ref = PQP_CPU.c compiled where it lay) or, if that library did not
+         travel, the oracle port; on a bounded sample; 1 thread (the reference has no threading).
+--impl reference: the same CPU code alone, on ALL host threads (one independent problem per thread).
 """
 from __future__ import annotations
 
