@@ -229,7 +229,7 @@ cudaError_t pqp_launch_fp(float *Fp, const float *Fp1, const float *Fp2, const f
 
 /*
  * Fd = GQ*Fp + Kp.  One output per thread, k ascending, separately rounded mul and add: the reference's order
- * (PQP_CPU.c:458-459), so Fd is bit-identical to the oracle's in every mode.  A block forms a 32-row x 32-problem tile of
+ * (PQP_CPU.c:458-459), so Fd is bit-identical to PQP_CPU.c's in every mode.  A block forms a 32-row x 32-problem tile of
  * outputs from shared-memory copies of the two operand tiles (coalesced loads; the k loop then reads a broadcast GQ value and a
  * conflict-free Fp column), instead of every thread walking its own strided row of GQ in global memory.
  */
