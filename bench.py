@@ -12,6 +12,7 @@ Workloads (BASELINE.json configs):
   c4            batched MPC: 4096 states per GPU sharing one Hessian (horizon 30, 12 states, 4 inputs, N=480);
                 a step is one batch solve of I updates; problems shard over ranks with no collective in the loop
                 and one NCCL all-gather of U at the end of every step (inside the timed region).
+  c5            the same shapes, 2^20 states IN TOTAL sharded contiguously over the ranks (strong scaling; BASELINE config 5).
 The c3 line also carries the c4 numbers under "batched" so one default run reports both headline metrics.
 
 value    whole-job throughput with inputs resident in HBM (PQP iterations/s for c2/c3, QP solves/s for c4).
@@ -43,6 +44,8 @@ WORKLOADS = {
     "c3": dict(kind="single", N=8192, M=2048, seed=12346),
     "c2": dict(kind="single", N=1024, M=512, seed=12345),
     "c4": dict(kind="batched", pH=30, nS=12, nI=4, B=4096, seed=2024),
+    # BASELINE config 5: 2^20 independent MPC problems in total, sharded contiguously over the ranks (strong scaling)
+    "c5": dict(kind="batched", pH=30, nS=12, nI=4, B_total=1 << 20, seed=2025),
 }
 
 
@@ -212,7 +215,7 @@ def run_reference(args, w, rank, world):
     engine, kind = cpu_engine()
     threads = host_threads()
     out = {"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+           "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
     if w["kind"] == "single":
         prob, d, Qd, Fd = single_problem_host(w)
         # memory: every replica builds its own two dense split matrices (8 N^2 bytes), as the reference does per call
@@ -247,7 +250,7 @@ def run_reference(args, w, rank, world):
         value = (threads * upd * args.steps / t) / args.iters  # solves/s at `iters` updates per solve
         sample = (f"{threads} threads x {upd} updates of one N={d.N} problem per step, scaled to {args.iters} updates per solve")
         out.update(metric="qp_solves_per_sec", unit="solves/s", value=value, ms_per_step=1e3 * t / args.steps,
-                   config={"workload": args.workload, "N": d.N, "M": d.M, "B": w["B"], "iters_per_solve": args.iters})
+                   config={"workload": args.workload, "N": d.N, "M": d.M, "B": w.get("B", w.get("B_total")), "iters_per_solve": args.iters})
     out["cpu_baseline"] = {"value": out["value"], "unit": out["unit"], "cores": threads, "kind": kind, "sample": sample}
     out["e2e"] = {"value": out["value"], "unit": out["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     out["gpu_launches"] = 0
@@ -369,17 +372,21 @@ def run_ours(args, w, rank, world, local_rank):
         s.close()
 
     if w["kind"] == "batched" or (args.workload == "c3" and not args.no_batched):
-        wb = WORKLOADS["c4"]
+        wb = w if w["kind"] == "batched" else WORKLOADS["c4"]
         from bench_problems import condensed_mpc, shard_range
-        B = wb["B"]
-        prob, d, Xall = condensed_mpc(wb["seed"], wb["pH"], wb["nS"], wb["nI"], n_states=B * world)
-        lo, hi = shard_range(B * world, world, rank)
+        strong = "B_total" in wb
+        total = wb["B_total"] if strong else wb["B"] * world
+        prob, d, Xall = condensed_mpc(wb["seed"], wb["pH"], wb["nS"], wb["nI"], n_states=total)
+        lo, hi = shard_range(total, world, rank)
+        if strong and total % world:
+            raise SystemExit("bench.py: c5 needs a rank count that divides 2^20")
+        B = hi - lo
         X = Xall[lo:hi]
         s = pqp.Solver(d, prob, device=local_rank, batch_capacity=B)
         X_dev = torch.from_numpy(X).cuda()
         Y_dev = torch.empty((B, d.N), dtype=torch.float32, device="cuda")
         U_dev = torch.empty((B, d.M), dtype=torch.float32, device="cuda")
-        U_all = torch.empty((B * world, d.M), dtype=torch.float32, device="cuda") if world > 1 else None
+        U_all = torch.empty((total, d.M), dtype=torch.float32, device="cuda") if world > 1 else None
         kern_ms = []
 
         def step_dev():
@@ -412,17 +419,19 @@ def run_ours(args, w, rank, world, local_rank):
         ms_e2e, _ = timed(step_e2e, s.stream)
         batched = {"metric": "qp_solves_per_sec", "unit": "solves/s", "value": solves, "ms_per_step": ms / args.steps,
                    "problem_iterations_per_sec": solves * args.iters,
-                   "config": {"workload": "c4", "N": d.N, "M": d.M, "B_per_gpu": B, "iters_per_solve": args.iters,
+                   "config": {"workload": "c5" if strong else "c4", "N": d.N, "M": d.M, "B_per_gpu": B, "B_total": total,
+                              "iters_per_solve": args.iters,
                               "kernel": s.last_kernel, "parallelism": f"problems sharded over {world} GPU(s), all-gather of U per step"},
                    "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "solves/s",
                            "h2d_bytes_per_step": int(X.nbytes), "d2h_bytes_per_step": int(Y_pin.numel() * 4 + U_pin.numel() * 4),
                            "call": "pqp_solve_batch_primal(host X -> host Y, U)"},
-                   "roofline": batched_roofline(s.last_kernel, tfl, k_ms, flop_iter, d.N, B, args.iters),
+                   "roofline": batched_roofline(s.last_kernel, tfl, k_ms, flop_iter, d.N, B, args.iters) | (
+                       {"traffic": None} if strong else {}),  # the committed ncu capture is of the c4 launch
                    "gpu_launches": int(launches)}
         s.close()
         if w["kind"] == "batched":
             result.update(metric=batched["metric"], unit=batched["unit"], value=batched["value"], ms_per_step=batched["ms_per_step"],
-                          config=batched["config"] | {"workload": "c4"}, e2e=batched["e2e"], roofline=batched["roofline"],
+                          config=batched["config"], e2e=batched["e2e"], roofline=batched["roofline"],
                           gpu_launches=batched["gpu_launches"], clocks=clocks_b)
             if rank == 0 and not args.no_cpu:
                 engine, kind = cpu_engine()
@@ -442,7 +451,7 @@ def run_ours(args, w, rank, world, local_rank):
     if rank == 0:
         line = {"metric": result.pop("metric"), "value": result.pop("value"), "unit": result.pop("unit"), "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": result.pop("ms_per_step"), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
+                "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
         line.update(result)
         print(json.dumps(line), flush=True)
 
