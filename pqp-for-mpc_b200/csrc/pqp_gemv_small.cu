@@ -232,9 +232,15 @@ int pqp_gemv_small_plan(int N, int ldq, int grid, int *wpr_out, int *cpt_out)
 	const int wpr = SM_WARPS / slots;
 	const int n4 = ldq / 4;
 	const int need = (n4 + 32 * wpr - 1) / (32 * wpr);
-	int cpt = 1;
-	while (cpt < need) cpt *= 2;
-	if (cpt > 16) return 0;
+	/* columns (float4) per thread: 8 of them live in registers, the rest in shared memory (up to 12 x 512 x 16 B = 96 KB) */
+	static const int choices[] = { 1, 2, 4, 8, 12, 16, 20 };
+	int cpt = 0;
+	for (unsigned i = 0; i < sizeof choices / sizeof choices[0]; i++)
+		if (choices[i] >= need) {
+			cpt = choices[i];
+			break;
+		}
+	if (!cpt) return 0;
 	*wpr_out = wpr;
 	*cpt_out = cpt;
 	return 1;
@@ -248,7 +254,9 @@ cudaError_t pqp_launch_gemv_small(const pqp_gemv_args *a, int wpr, int cpt, void
 	case 2: fn = (const void *)gemv_small_kernel<2>; break;
 	case 4: fn = (const void *)gemv_small_kernel<4>; break;
 	case 8: fn = (const void *)gemv_small_kernel<8>; break;
+	case 12: fn = (const void *)gemv_small_kernel<12>; break;
 	case 16: fn = (const void *)gemv_small_kernel<16>; break;
+	case 20: fn = (const void *)gemv_small_kernel<20>; break;
 	default: return cudaErrorInvalidValue;
 	}
 	cudaError_t e = cudaMemsetAsync(a->barrier, 0, sizeof(unsigned), s);
