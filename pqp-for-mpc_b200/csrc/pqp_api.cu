@@ -217,7 +217,7 @@ static int finish_setup(pqp_handle *h)
 		if (v >= 1 && v <= h->num_sms && v <= N) grid = v;
 	}
 	h->gemv_grid = grid;
-	if ((rc = dalloc(&h->partials, (size_t)2 * grid * 8))) return rc;
+	if ((rc = dalloc(&h->partials, (size_t)2 * h->num_sms * 16))) return rc; /* per-CTA evaluation slots / check packets of the loop kernels */
 	/* rows of each slab that fit in shared memory next to y and the partial sums */
 	size_t base;
 	pqp_gemv_smem_bytes(N, ldq, grid, 0, &base);
@@ -522,8 +522,9 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 	}
 
 	if (h->gemv_grid <= 0) return PQP_ERR_UNSUPPORTED;
-	if (iters > 0 && h->small_ok) {
-		h->last_kernel = "gemv_small_registers";
+	if (h->small_ok && !(iters <= 0 && getenv("PQP_GEMV_SMALL_TOL") && atoi(getenv("PQP_GEMV_SMALL_TOL")) == 0)) {
+		/* fixed count, or run to tolerance with the stop test evaluated in the kernel every check_every updates */
+		h->last_kernel = iters > 0 ? "gemv_small_registers" : "gemv_small_registers_tol";
 		a.grid = h->small_grid;
 		CK(pqp_launch_gemv_small(&a, h->small_wpr, h->small_cpt, h->pk0, h->pk1, h->stream));
 		h->launches++;

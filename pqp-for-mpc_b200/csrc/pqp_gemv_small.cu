@@ -70,7 +70,13 @@ __device__ __forceinline__ void sm_grid_barrier(unsigned *counter, unsigned &tar
 	__syncthreads();
 }
 
-template <int CPT>
+/*
+ * TOL = true: run to the stop test (a.iters <= 0).  Every a.check_every passes (and at a.max_iters) the pass first evaluates
+ * the stop test of terminate() on g = den - num = Qd y + Fd BEFORE applying its update: per-CTA partial results
+ * travel as {value, epoch} packets like y does, every CTA folds all of them in the same order and so takes the same decision;
+ * a converged problem leaves with exactly the y that passed.  One extra L2 round trip per check, none per update.
+ */
+template <int CPT, bool TOL>
 __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gemv_args a, int wpr, uint2 *pk0, uint2 *pk1)
 {
 	extern __shared__ __align__(16) float y_s[]; /* [2][ldq]: y of the current / next pass */
@@ -106,11 +112,14 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 		fd_r = a.Fd[row];
 		if (a.Kp) kp_tol = fmaxf(a.erc * a.Kp[row], a.eac);
 	}
-	const int passes = a.iters + 1;
+	const int passes = TOL ? a.max_iters + 1 : a.iters + 1;
 	unsigned bar_target = 0;
+	__shared__ int stop_s;
+	uint2 *cpk = reinterpret_cast<uint2 *>(a.partials); /* TOL: [2][G][5] check packets */
+	float *fin = a.partials + (TOL ? (size_t)2 * G * 10 : 0); /* final per-CTA slots, clear of packets a slow CTA may still be polling */
 
 	for (int p = 0; p < passes; p++) {
-		const bool is_last = (p == passes - 1);
+		bool is_last = (p == passes - 1);
 		const uint2 *pk_in = (p & 1) ? pk1 : pk0;
 		uint2 *pk_out = (p & 1) ? pk0 : pk1;
 		/* all threads: fetch y of this pass (packets -> plain floats in shared memory), once per CTA */
@@ -165,6 +174,50 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 			const float y_mine = y_s[(size_t)(p & 1) * ldq + row];
 			num = fmaf(th_r, y_mine, num) + fmaxf(-fd_r, 0.0f);
 			den = fmaf(th_r, y_mine, den) + fmaxf(fd_r, 0.0f);
+		}
+		if (TOL && !is_last && (p % a.check_every) == 0) {
+			/* ---- the stop test on y_p, before y_{p+1} is published ---- */
+			const unsigned chk = (unsigned)(p / a.check_every) + 1u;
+			if (finisher) {
+				const float y_mine = y_s[(size_t)(p & 1) * ldq + row];
+				const float gq = den - num;
+				e_min = gq; e_gap = y_mine * gq; e_jd = y_mine * (0.5f * (gq + fd_r)); e_viol = -gq - kp_tol;
+			}
+			if (lane == 0) {
+				ev_s[warp][0] = e_min; ev_s[warp][1] = e_gap; ev_s[warp][2] = e_jd; ev_s[warp][4] = e_viol;
+			}
+			__syncthreads();
+			uint2 *mine = cpk + ((size_t)(chk & 1u) * G + blockIdx.x) * 5;
+			if (tid == 0) {
+				float m = ev_s[0][0], ga = ev_s[0][1], jd = ev_s[0][2], vi = ev_s[0][4];
+				for (int w = 1; w < SM_WARPS; w++) {
+					m = fminf(m, ev_s[w][0]); ga += ev_s[w][1]; jd += ev_s[w][2]; vi = fmaxf(vi, ev_s[w][4]);
+				}
+				sm_st_packet(mine + 0, m, chk); sm_st_packet(mine + 1, ga, chk); sm_st_packet(mine + 2, jd, chk); sm_st_packet(mine + 4, vi, chk);
+			}
+			if (warp == 0) {
+				float v_min = INFINITY, v_gap = 0.0f, v_jd = 0.0f, v_viol = -INFINITY;
+				for (unsigned c = lane; c < G; c += 32) {
+					const uint2 *sl = cpk + ((size_t)(chk & 1u) * G + c) * 5;
+					v_min = fminf(v_min, sm_ld_packet(sl + 0, chk)); v_gap += sm_ld_packet(sl + 1, chk); v_jd += sm_ld_packet(sl + 2, chk);
+					v_viol = fmaxf(v_viol, sm_ld_packet(sl + 4, chk));
+				}
+#pragma unroll
+				for (int o = 16; o; o >>= 1) {
+					v_min = fminf(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
+					v_gap += __shfl_xor_sync(0xffffffffu, v_gap, o);
+					v_jd += __shfl_xor_sync(0xffffffffu, v_jd, o);
+					v_viol = fmaxf(v_viol, __shfl_xor_sync(0xffffffffu, v_viol, o));
+				}
+				const float Jd = v_jd + (a.Md ? 0.5f * a.Md[0] : 0.0f);
+				if (lane == 0) stop_s = (v_viol <= 0.0f && fabsf(v_gap) <= a.eaj && fabsf(v_gap) <= a.erj * fabsf(Jd)) ? 1 : 0;
+			}
+			__syncthreads();
+			if (stop_s) is_last = true; /* uniform across the grid: every CTA folded the same packets in the same order */
+			e_min = INFINITY; e_gap = 0.0f; e_jd = 0.0f; e_viol = -INFINITY;
+		}
+		if (finisher) {
+			const float y_mine = y_s[(size_t)(p & 1) * ldq + row];
 			if (!is_last) {
 				sm_st_packet(pk_out + row, __fdiv_rn(num, den) * y_mine, (uint32_t)(p + 1));
 			} else {
@@ -187,7 +240,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 					e_min = fminf(e_min, ev_s[w][0]); e_gap += ev_s[w][1]; e_jd += ev_s[w][2];
 					e_kkt = fmaxf(e_kkt, ev_s[w][3]); e_viol = fmaxf(e_viol, ev_s[w][4]);
 				}
-				float *sl = a.partials + (size_t)blockIdx.x * 8;
+				float *sl = fin + (size_t)blockIdx.x * 8;
 				sl[0] = e_min; sl[1] = e_gap; sl[2] = e_jd; sl[3] = e_kkt; sl[4] = e_viol;
 				__threadfence();
 			}
@@ -195,7 +248,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 			if (blockIdx.x == 0 && warp == 0) {
 				float v_min = INFINITY, v_gap = 0.0f, v_jd = 0.0f, v_kkt = 0.0f;
 				for (unsigned c = lane; c < G; c += 32) {
-					const float *sl = a.partials + (size_t)c * 8;
+					const float *sl = fin + (size_t)c * 8;
 					v_min = fminf(v_min, __ldcg(sl + 0)); v_gap += __ldcg(sl + 1); v_jd += __ldcg(sl + 2);
 					v_kkt = fmaxf(v_kkt, __ldcg(sl + 3));
 				}
@@ -208,8 +261,8 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 				}
 				if (lane == 0) {
 					pqp_status o;
-					o.iters = a.iters;
-					o.converged = 0;
+					o.iters = TOL ? p : a.iters;
+					o.converged = (TOL && p < passes - 1) ? 1 : 0;
 					o.min_slack = v_min;
 					o.gap = v_gap;
 					o.Jd = v_jd + (a.Md ? 0.5f * a.Md[0] : 0.0f);
@@ -218,6 +271,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 					*a.result_buf = 1;
 				}
 			}
+			break; /* TOL: the pass that passed the test is the last one */
 		}
 	}
 }
@@ -246,20 +300,26 @@ int pqp_gemv_small_plan(int N, int ldq, int grid, int *wpr_out, int *cpt_out)
 	return 1;
 }
 
+template <bool TOL> static const void *small_fn(int cpt)
+{
+	switch (cpt) {
+	case 1: return (const void *)gemv_small_kernel<1, TOL>;
+	case 2: return (const void *)gemv_small_kernel<2, TOL>;
+	case 4: return (const void *)gemv_small_kernel<4, TOL>;
+	case 8: return (const void *)gemv_small_kernel<8, TOL>;
+	case 12: return (const void *)gemv_small_kernel<12, TOL>;
+	case 16: return (const void *)gemv_small_kernel<16, TOL>;
+	case 20: return (const void *)gemv_small_kernel<20, TOL>;
+	default: return NULL;
+	}
+}
+
 cudaError_t pqp_launch_gemv_small(const pqp_gemv_args *a, int wpr, int cpt, void *pk0, void *pk1, cudaStream_t s)
 {
-	const void *fn = NULL;
-	switch (cpt) {
-	case 1: fn = (const void *)gemv_small_kernel<1>; break;
-	case 2: fn = (const void *)gemv_small_kernel<2>; break;
-	case 4: fn = (const void *)gemv_small_kernel<4>; break;
-	case 8: fn = (const void *)gemv_small_kernel<8>; break;
-	case 12: fn = (const void *)gemv_small_kernel<12>; break;
-	case 16: fn = (const void *)gemv_small_kernel<16>; break;
-	case 20: fn = (const void *)gemv_small_kernel<20>; break;
-	default: return cudaErrorInvalidValue;
-	}
+	const void *fn = a->iters > 0 ? small_fn<false>(cpt) : small_fn<true>(cpt);
+	if (!fn) return cudaErrorInvalidValue;
 	cudaError_t e = cudaMemsetAsync(a->barrier, 0, sizeof(unsigned), s);
+	if (e == cudaSuccess && a->iters <= 0) e = cudaMemsetAsync(a->partials, 0, (size_t)2 * a->grid * 5 * sizeof(uint2), s); /* check packets: epoch 0 = none */
 	if (e == cudaSuccess) e = cudaMemsetAsync(pk0, 0xFF, (size_t)a->ldq * sizeof(uint2), s);
 	if (e == cudaSuccess) e = cudaMemsetAsync(pk1, 0xFF, (size_t)a->ldq * sizeof(uint2), s);
 	if (e != cudaSuccess) return e;

@@ -306,3 +306,24 @@ def test_reference_main_flow_through_the_compat_library(pqp, gold_example):
     ref_u = [float(t) for t in str(gold_example["stdout"]).split("Printing U*")[1].split()]
     got_u = [float(t) for t in fast.stdout.split("Printing U*")[1].split()]
     assert np.allclose(got_u, ref_u, atol=2e-5)
+
+
+def test_single_problem_run_to_tolerance_on_chip(pqp):
+    """iters <= 0 for a problem that lives on chip (N <= 2368): the register kernel evaluates the stop test itself every
+    check_every updates (no host round trip, one extra L2 exchange per check) and leaves with exactly the y that passed:
+    bit-identical to the fixed-count solve at the reported count."""
+    prob, d = pqp.generate_testproblem(77, 1200, 600)
+    with pqp.Solver(d, prob, eaj=1e-2, erj=1e-6, check_every=8, max_iters=200000) as s:
+        Y, U, st = s.solve(iters=0, primal=True)
+        assert s.last_kernel == "gemv_small_registers_tol"
+        assert st["converged"][0] == 1 and st["iters"][0] % 8 == 0 and 8 <= st["iters"][0] < 200000
+        assert abs(st["gap"][0]) <= 1e-2 and st["min_slack"][0] >= -1e-3
+        Yf, Uf, stf = s.solve(iters=int(st["iters"][0]), primal=True)
+        assert s.last_kernel == "gemv_small_registers"
+        assert np.array_equal(Y, Yf) and np.array_equal(U, Uf)
+        assert abs(stf["Jd"][0] - st["Jd"][0]) <= 1e-6 * abs(st["Jd"][0])
+    with pqp.Solver(d, prob, eaj=1e-2, erj=1e-6, check_every=8, max_iters=40) as s:
+        Y, _, st = s.solve(iters=0)                                   # the cap: unconverged after exactly max_iters updates
+        assert st["converged"][0] == 0 and st["iters"][0] == 40
+        Yf, _, _ = s.solve(iters=40)
+        assert np.array_equal(Y, Yf)
