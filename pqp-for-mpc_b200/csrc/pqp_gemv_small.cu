@@ -19,6 +19,11 @@
  */
 #include "pqp_internal.h"
 
+#include <type_traits>
+
+#ifndef SMALL_TOL_DBG
+#define SMALL_TOL_DBG 0 /* experiment switch: 1 no decision read, 2 no check publish */
+#endif
 #define SM_THREADS 512
 #define SM_WARPS 16
 
@@ -44,6 +49,22 @@ __device__ __forceinline__ float4 sm_ld_packet4(const uint2 *src, uint32_t epoch
 		if (e0 == epoch && e1 == epoch && e2 == epoch && e3 == epoch) break;
 	}
 	return make_float4(__uint_as_float(a0), __uint_as_float(a1), __uint_as_float(a2), __uint_as_float(a3));
+}
+/* two values and their epochs in one 16-byte store / polling load */
+__device__ __forceinline__ void sm_st_packet2(uint4 *dst, float v0, float v1, uint32_t epoch)
+{
+	asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(__float_as_uint(v0)), "r"(epoch), "r"(__float_as_uint(v1)), "r"(epoch)
+		     : "memory");
+}
+__device__ __forceinline__ void sm_ld_packet2(const uint4 *src, uint32_t epoch, float &v0, float &v1)
+{
+	uint32_t a0, e0, a1, e1;
+	for (;;) {
+		asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(e0), "=r"(a1), "=r"(e1) : "l"(src) : "memory");
+		if (e0 == epoch && e1 == epoch) break;
+	}
+	v0 = __uint_as_float(a0);
+	v1 = __uint_as_float(a1);
 }
 __device__ __forceinline__ void sm_acc4(float &num, float &den, const float4 q, const float4 y)
 {
@@ -114,12 +135,15 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 	}
 	const int passes = TOL ? a.max_iters + 1 : a.iters + 1;
 	unsigned bar_target = 0;
-	__shared__ int stop_s;
-	uint2 *cpk = reinterpret_cast<uint2 *>(a.partials); /* TOL: [2][G][5] check packets */
-	float *fin = a.partials + (TOL ? (size_t)2 * G * 10 : 0); /* final per-CTA slots, clear of packets a slow CTA may still be polling */
+	uint4 *cpk4 = reinterpret_cast<uint4 *>(a.partials); /* TOL: [2][G][3] check packets of 16 bytes */
+	float *fin = a.partials + (TOL ? (size_t)2 * G * 12 : 0); /* final per-CTA slots, clear of packets a slow CTA may still be polling */
+	__shared__ float chk_s[TOL ? 148 : 1][6];
 
-	for (int p = 0; p < passes; p++) {
-		bool is_last = (p == passes - 1);
+	/* one pass; CHK / DEC are compile-time so that the plain pass carries none of the stop-test code (with runtime flags the
+	 * skipped blocks still cost 0.7 us per pass).  Returns true when the kernel is done. */
+	auto pass = [&](const int p, auto chk_c, auto dec_c) -> bool {
+		constexpr bool CHK = decltype(chk_c)::value, DEC = decltype(dec_c)::value;
+		const bool is_last = (p == passes - 1);
 		const uint2 *pk_in = (p & 1) ? pk1 : pk0;
 		uint2 *pk_out = (p & 1) ? pk0 : pk1;
 		/* all threads: fetch y of this pass (packets -> plain floats in shared memory), once per CTA */
@@ -138,7 +162,45 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 			}
 			ys4[c] = y4;
 		}
+		constexpr bool decide = TOL && DEC;
+		if (decide && tid < 3 * (int)G) {
+			/* the stop test of pass p-1: one 16-byte polling load per thread, all in flight at once */
+			const unsigned chk = (unsigned)((p - 1) / a.check_every) + 1u;
+			const int c = tid / 3, k = tid % 3;
+			float v0, v1;
+			sm_ld_packet2(cpk4 + ((size_t)(chk & 1u) * G + c) * 3 + k, chk, v0, v1);
+			chk_s[c][2 * k] = v0;
+			chk_s[c][2 * k + 1] = v1;
+		}
 		__syncthreads();
+		if (decide) {
+			/* every warp of every CTA folds all CTAs' values in the same order, so all take the same decision */
+			float v_min = INFINITY, v_gap = 0.0f, v_jd = 0.0f, v_kkt = 0.0f, v_viol = -INFINITY;
+			for (unsigned c = lane; c < G; c += 32) {
+				v_min = fminf(v_min, chk_s[c][0]); v_gap += chk_s[c][1]; v_jd += chk_s[c][2]; v_kkt = fmaxf(v_kkt, chk_s[c][3]);
+				v_viol = fmaxf(v_viol, chk_s[c][4]);
+			}
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				v_min = fminf(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
+				v_gap += __shfl_xor_sync(0xffffffffu, v_gap, o);
+				v_jd += __shfl_xor_sync(0xffffffffu, v_jd, o);
+				v_kkt = fmaxf(v_kkt, __shfl_xor_sync(0xffffffffu, v_kkt, o));
+				v_viol = fmaxf(v_viol, __shfl_xor_sync(0xffffffffu, v_viol, o));
+			}
+			const float Jd = v_jd + (a.Md ? 0.5f * a.Md[0] : 0.0f);
+			if (v_viol <= 0.0f && fabsf(v_gap) <= a.eaj && fabsf(v_gap) <= a.erj * fabsf(Jd)) {
+				/* converged at y_{p-1}, which still sits in the other half of the double-buffered shared copy */
+				if (finisher) a.ybuf1[row] = y_s[(size_t)((p - 1) & 1) * ldq + row];
+				if (blockIdx.x == 0 && tid == 0) {
+					pqp_status o;
+					o.iters = p - 1; o.converged = 1; o.min_slack = v_min; o.gap = v_gap; o.Jd = Jd; o.kkt = v_kkt;
+					*a.status = o;
+					*a.result_buf = 1;
+				}
+				return true; /* uniform across the grid */
+			}
+		}
 		float num0 = 0.0f, den0 = 0.0f, num1 = 0.0f, den1 = 0.0f;
 #pragma unroll
 		for (int u = 0; u < CPT; u++) {
@@ -175,46 +237,30 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 			num = fmaf(th_r, y_mine, num) + fmaxf(-fd_r, 0.0f);
 			den = fmaf(th_r, y_mine, den) + fmaxf(fd_r, 0.0f);
 		}
-		if (TOL && !is_last && (p % a.check_every) == 0) {
-			/* ---- the stop test on y_p, before y_{p+1} is published ---- */
+		if (TOL && CHK && !is_last) {
+			/* ---- publish this CTA's share of the stop test on y_p; the decision is read at the start of the NEXT pass, when
+			 * the packets have long arrived (no exchange latency added), and y_{p+1} is published below as always ---- */
 			const unsigned chk = (unsigned)(p / a.check_every) + 1u;
 			if (finisher) {
 				const float y_mine = y_s[(size_t)(p & 1) * ldq + row];
 				const float gq = den - num;
-				e_min = gq; e_gap = y_mine * gq; e_jd = y_mine * (0.5f * (gq + fd_r)); e_viol = -gq - kp_tol;
+				e_min = gq; e_gap = y_mine * gq; e_jd = y_mine * (0.5f * (gq + fd_r)); e_kkt = fabsf(fminf(y_mine, gq)); e_viol = -gq - kp_tol;
 			}
 			if (lane == 0) {
-				ev_s[warp][0] = e_min; ev_s[warp][1] = e_gap; ev_s[warp][2] = e_jd; ev_s[warp][4] = e_viol;
+				ev_s[warp][0] = e_min; ev_s[warp][1] = e_gap; ev_s[warp][2] = e_jd; ev_s[warp][3] = e_kkt; ev_s[warp][4] = e_viol;
 			}
 			__syncthreads();
-			uint2 *mine = cpk + ((size_t)(chk & 1u) * G + blockIdx.x) * 5;
 			if (tid == 0) {
-				float m = ev_s[0][0], ga = ev_s[0][1], jd = ev_s[0][2], vi = ev_s[0][4];
+				float m = ev_s[0][0], ga = ev_s[0][1], jd = ev_s[0][2], kk = ev_s[0][3], vi = ev_s[0][4];
 				for (int w = 1; w < SM_WARPS; w++) {
-					m = fminf(m, ev_s[w][0]); ga += ev_s[w][1]; jd += ev_s[w][2]; vi = fmaxf(vi, ev_s[w][4]);
+					m = fminf(m, ev_s[w][0]); ga += ev_s[w][1]; jd += ev_s[w][2]; kk = fmaxf(kk, ev_s[w][3]); vi = fmaxf(vi, ev_s[w][4]);
 				}
-				sm_st_packet(mine + 0, m, chk); sm_st_packet(mine + 1, ga, chk); sm_st_packet(mine + 2, jd, chk); sm_st_packet(mine + 4, vi, chk);
+				uint4 *mine = cpk4 + ((size_t)(chk & 1u) * G + blockIdx.x) * 3; /* {value, epoch, value, epoch} x 3, one 16-byte store each */
+				sm_st_packet2(mine + 0, m, ga, chk);
+				sm_st_packet2(mine + 1, jd, kk, chk);
+				sm_st_packet2(mine + 2, vi, 0.0f, chk);
 			}
-			if (warp == 0) {
-				float v_min = INFINITY, v_gap = 0.0f, v_jd = 0.0f, v_viol = -INFINITY;
-				for (unsigned c = lane; c < G; c += 32) {
-					const uint2 *sl = cpk + ((size_t)(chk & 1u) * G + c) * 5;
-					v_min = fminf(v_min, sm_ld_packet(sl + 0, chk)); v_gap += sm_ld_packet(sl + 1, chk); v_jd += sm_ld_packet(sl + 2, chk);
-					v_viol = fmaxf(v_viol, sm_ld_packet(sl + 4, chk));
-				}
-#pragma unroll
-				for (int o = 16; o; o >>= 1) {
-					v_min = fminf(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
-					v_gap += __shfl_xor_sync(0xffffffffu, v_gap, o);
-					v_jd += __shfl_xor_sync(0xffffffffu, v_jd, o);
-					v_viol = fmaxf(v_viol, __shfl_xor_sync(0xffffffffu, v_viol, o));
-				}
-				const float Jd = v_jd + (a.Md ? 0.5f * a.Md[0] : 0.0f);
-				if (lane == 0) stop_s = (v_viol <= 0.0f && fabsf(v_gap) <= a.eaj && fabsf(v_gap) <= a.erj * fabsf(Jd)) ? 1 : 0;
-			}
-			__syncthreads();
-			if (stop_s) is_last = true; /* uniform across the grid: every CTA folded the same packets in the same order */
-			e_min = INFINITY; e_gap = 0.0f; e_jd = 0.0f; e_viol = -INFINITY;
+			e_min = INFINITY; e_gap = 0.0f; e_jd = 0.0f; e_kkt = 0.0f; e_viol = -INFINITY;
 		}
 		if (finisher) {
 			const float y_mine = y_s[(size_t)(p & 1) * ldq + row];
@@ -262,7 +308,7 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 				if (lane == 0) {
 					pqp_status o;
 					o.iters = TOL ? p : a.iters;
-					o.converged = (TOL && p < passes - 1) ? 1 : 0;
+					o.converged = 0; /* TOL: this block is only reached at the cap; a converged run left at the decision above */
 					o.min_slack = v_min;
 					o.gap = v_gap;
 					o.Jd = v_jd + (a.Md ? 0.5f * a.Md[0] : 0.0f);
@@ -271,7 +317,28 @@ __global__ void __launch_bounds__(SM_THREADS, 1) gemv_small_kernel(const pqp_gem
 					*a.result_buf = 1;
 				}
 			}
-			break; /* TOL: the pass that passed the test is the last one */
+			return true;
+		}
+		return false;
+	};
+
+	if (!TOL) {
+		for (int p = 0; p < passes; p++)
+			if (pass(p, std::false_type{}, std::false_type{})) break;
+	} else {
+		/* check passes at p = 0, check_every, 2*check_every, ...; the decision of a check is read at the start of the next pass */
+		int next_chk = 0;
+		bool pending = false;
+		for (int p = 0; p < passes; p++) {
+			const bool chk = (p == next_chk);
+			bool done;
+			if (chk && pending) done = pass(p, std::true_type{}, std::true_type{});
+			else if (chk) done = pass(p, std::true_type{}, std::false_type{});
+			else if (pending) done = pass(p, std::false_type{}, std::true_type{});
+			else done = pass(p, std::false_type{}, std::false_type{});
+			if (done) break;
+			pending = chk;
+			if (chk) next_chk += a.check_every;
 		}
 	}
 }
@@ -319,7 +386,7 @@ cudaError_t pqp_launch_gemv_small(const pqp_gemv_args *a, int wpr, int cpt, void
 	const void *fn = a->iters > 0 ? small_fn<false>(cpt) : small_fn<true>(cpt);
 	if (!fn) return cudaErrorInvalidValue;
 	cudaError_t e = cudaMemsetAsync(a->barrier, 0, sizeof(unsigned), s);
-	if (e == cudaSuccess && a->iters <= 0) e = cudaMemsetAsync(a->partials, 0, (size_t)2 * a->grid * 5 * sizeof(uint2), s); /* check packets: epoch 0 = none */
+	if (e == cudaSuccess && a->iters <= 0) e = cudaMemsetAsync(a->partials, 0, (size_t)2 * a->grid * 3 * sizeof(uint4), s); /* check packets: epoch 0 = none */
 	if (e == cudaSuccess) e = cudaMemsetAsync(pk0, 0xFF, (size_t)a->ldq * sizeof(uint2), s);
 	if (e == cudaSuccess) e = cudaMemsetAsync(pk1, 0xFF, (size_t)a->ldq * sizeof(uint2), s);
 	if (e != cudaSuccess) return e;
