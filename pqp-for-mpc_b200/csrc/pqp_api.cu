@@ -59,6 +59,8 @@ struct pqp_handle {
 	int gemv_grid, gemv_resident;
 	int tma_ok, tma_stages, tma_resident, tma_yc, tma_pinned;
 	int small_ok, small_wpr, small_cpt, small_grid;
+	int sym_state; /* 0 not examined, 1 Qd symmetric and the unit array built, -1 unavailable */
+	pqp_sym_plan sym;
 	int l2_window_set;
 	long long launches;
 	const char *last_kernel;
@@ -450,7 +452,8 @@ void pqp_destroy(pqp_handle *h)
 	}
 	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
 			 h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
-			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf, h->pk0, h->pk1 };
+			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf, h->pk0, h->pk1,
+			 h->sym.units, h->sym.cta_u0, h->sym.cta_j0, h->sym.strip_c0, h->sym.strip_c1, h->sym.rowpart, h->sym.colpart };
 	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
 		if (ptrs[i]) cudaFree(ptrs[i]);
 	if (h->ev0) cudaEventDestroy(h->ev0);
@@ -461,6 +464,89 @@ void pqp_destroy(pqp_handle *h)
 }
 
 /* ---- the loop -------------------------------------------------------------------------------- */
+
+/*
+ * The upper-triangle loop (pqp_gemv_sym.cu) needs Qd symmetric element for element; examined once per handle, on the
+ * first single-problem fixed-count solve that could use it.  Returns PQP_OK with h->sym_state set to 1 or -1.
+ */
+static int ensure_sym(pqp_handle *h)
+{
+	if (h->sym_state) return PQP_OK;
+	h->sym_state = -1;
+	const int N = h->d.N, G = h->gemv_grid;
+	const char *e;
+	if ((e = getenv("PQP_GEMV_SYM")) && atoi(e) == 0) return PQP_OK;
+	if (h->o.order == PQP_ORDER_STRICT || G <= 0 || h->small_ok) return PQP_OK;
+	const size_t budget = h->smem_optin > 1024 ? h->smem_optin - 1024 : 0;
+	pqp_sym_plan pl;
+	memset(&pl, 0, sizeof pl);
+	if (!pqp_gemv_sym_plan(N, G, budget, &pl.stages, &pl.resident)) return PQP_OK;
+	unsigned *bad_dev = NULL, bad = 1;
+	int rc;
+	if ((rc = dalloc(&bad_dev, 1))) return rc;
+	CK(pqp_launch_sym_check(h->Q, h->ldq, N, bad_dev, h->stream));
+	h->launches++;
+	CK(cudaMemcpyAsync(&bad, bad_dev, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
+	CK(cudaStreamSynchronize(h->stream));
+	cudaFree(bad_dev);
+	if (getenv("PQP_VERBOSE")) fprintf(stderr, "pqp: symmetry test of Qd: %u unequal pairs\n", bad);
+	if (bad) return PQP_OK;
+
+	pqp_gemv_sym_counts(N, &pl.nb, &pl.U);
+	int *tab = (int *)malloc(sizeof(int) * ((size_t)2 * G + 1 + 2 * (size_t)pl.nb));
+	if (!tab) return PQP_ERR_ALLOC;
+	int *cta_u0 = tab, *cta_j0 = tab + G + 1, *strip_c0 = cta_j0 + G, *strip_c1 = strip_c0 + pl.nb;
+	pl.maxseg = pqp_gemv_sym_tables(N, G, cta_u0, cta_j0, strip_c0, strip_c1);
+	const int umax = (pl.U + G - 1) / G;
+	if ((e = getenv("PQP_SYM_RESIDENT"))) {
+		int v = atoi(e);
+		if (v >= 0 && v < pl.resident) pl.resident = v;
+	}
+	/* streamed units per CTA fetched evict_last: everything when the streamed part of the triangle fits in ~80% of L2, else a
+	 * fraction of L2 spread evenly over the CTAs */
+	int l2_bytes = 0;
+	cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, h->device);
+	const int streamed = umax - pl.resident > 0 ? umax - pl.resident : 0;
+	const double unit_bytes = 64.0 * 128.0 * 4.0;
+	double frac = 0.6;
+	if ((e = getenv("PQP_SYM_PIN_FRAC"))) frac = atof(e);
+	pl.pinned = streamed;
+	if ((double)streamed * G * unit_bytes > 0.8 * (double)l2_bytes) pl.pinned = (int)(frac * (double)l2_bytes / ((double)G * unit_bytes));
+	if (!h->o.l2_persist) pl.pinned = 0;
+	if ((e = getenv("PQP_SYM_PIN"))) pl.pinned = atoi(e) > 0 ? atoi(e) : 0;
+
+	const size_t nT = (size_t)pl.nb * (pl.nb + 1) / 2;
+	pl.rowpart_bytes = 2 * nT * 128 * 16;
+	pl.colpart_bytes = 2 * (size_t)G * pl.maxseg * 128 * 16;
+	unsigned char *rp = NULL, *cp = NULL;
+	if ((rc = dalloc(&pl.units, pqp_gemv_sym_units_bytes(N) / sizeof(float))) || (rc = dalloc(&pl.cta_u0, (size_t)G + 1)) ||
+	    (rc = dalloc(&pl.cta_j0, (size_t)G)) || (rc = dalloc(&pl.strip_c0, (size_t)pl.nb)) || (rc = dalloc(&pl.strip_c1, (size_t)pl.nb)) ||
+	    (rc = dalloc(&rp, pl.rowpart_bytes)) || (rc = dalloc(&cp, pl.colpart_bytes))) {
+		free(tab);
+		void *ptrs[] = { pl.units, pl.cta_u0, pl.cta_j0, pl.strip_c0, pl.strip_c1, rp, cp };
+		for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
+			if (ptrs[i]) cudaFree(ptrs[i]);
+		cudaGetLastError();
+		return PQP_OK; /* no room for the second copy of the triangle: the full-matrix kernels still run */
+	}
+	pl.rowpart = rp;
+	pl.colpart = cp;
+	cudaMemcpyAsync(pl.cta_u0, cta_u0, sizeof(int) * ((size_t)G + 1), cudaMemcpyHostToDevice, h->stream);
+	cudaMemcpyAsync(pl.cta_j0, cta_j0, sizeof(int) * (size_t)G, cudaMemcpyHostToDevice, h->stream);
+	cudaMemcpyAsync(pl.strip_c0, strip_c0, sizeof(int) * (size_t)pl.nb, cudaMemcpyHostToDevice, h->stream);
+	cudaMemcpyAsync(pl.strip_c1, strip_c1, sizeof(int) * (size_t)pl.nb, cudaMemcpyHostToDevice, h->stream);
+	cudaError_t ce = pqp_launch_build_sym_units(pl.units, h->Q, h->ldq, N, h->stream);
+	if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+	free(tab);
+	h->sym = pl; /* owned by the handle from here on (freed in pqp_destroy) */
+	CK(ce);
+	h->launches++;
+	if (getenv("PQP_VERBOSE"))
+		fprintf(stderr, "pqp: gemv_sym N=%d grid=%d units=%d (%d per CTA) stages=%d resident=%d pinned=%d maxseg=%d\n", N, G, pl.U, umax,
+			pl.stages, pl.resident, pl.pinned, pl.maxseg);
+	h->sym_state = 1;
+	return PQP_OK;
+}
 
 /* one problem: Fd (device, N), y0 (device N, or NULL -> y_init); result left in *y_res (device) */
 static int run_single(pqp_handle *h, const float *Fd, const float *Md, const float *y0, int iters, const float **y_res,
@@ -530,6 +616,17 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		h->launches++;
 		*y_res = h->ybuf1;
 		return PQP_OK;
+	}
+	if (iters > 0) {
+		int rc = ensure_sym(h);
+		if (rc) return rc;
+		if (h->sym_state == 1) {
+			h->last_kernel = h->sym.resident >= (h->sym.U + h->gemv_grid - 1) / h->gemv_grid ? "gemv_sym_resident" : "gemv_sym_stream";
+			CK(pqp_launch_gemv_sym(&a, &h->sym, h->pk0, h->pk1, h->stream));
+			h->launches++;
+			*y_res = h->ybuf1;
+			return PQP_OK;
+		}
 	}
 	if (iters > 0 && h->tma_ok) {
 		h->last_kernel = h->tma_resident >= (N + h->gemv_grid - 1) / h->gemv_grid + 1 ? "gemv_tma_resident" : "gemv_tma_stream";

@@ -85,6 +85,22 @@ cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident
 /* register-resident variant for small N (pqp_gemv_small.cu); result left in ybuf1 */
 int pqp_gemv_small_plan(int N, int ldq, int grid, int *wpr, int *cpt);
 cudaError_t pqp_launch_gemv_small(const pqp_gemv_args *a, int wpr, int cpt, void *pk0, void *pk1, cudaStream_t s);
+/* upper-triangle variant for a symmetric Qd (pqp_gemv_sym.cu), fixed-count solves; result left in ybuf1 */
+typedef struct pqp_sym_plan {
+	int nb, U, maxseg;           /* 128-wide blocks, 64x128 units of the upper triangle, most strips one CTA touches */
+	int stages, resident, pinned;
+	float *units;                /* device [U][64][128] */
+	int *cta_u0, *cta_j0, *strip_c0, *strip_c1; /* device tables (pqp_gemv_sym_tables) */
+	void *rowpart, *colpart;     /* device packet arrays */
+	size_t rowpart_bytes, colpart_bytes;
+} pqp_sym_plan;
+void pqp_gemv_sym_counts(int N, int *nb, int *U);
+size_t pqp_gemv_sym_units_bytes(int N);
+int pqp_gemv_sym_plan(int N, int grid, size_t smem_budget, int *stages, int *resident);
+int pqp_gemv_sym_tables(int N, int G, int *cta_u0, int *cta_j0, int *strip_c0, int *strip_c1);
+cudaError_t pqp_launch_sym_check(const float *Q, int ldq, int N, unsigned *mismatch, cudaStream_t s);
+cudaError_t pqp_launch_build_sym_units(float *units, const float *Q, int ldq, int N, cudaStream_t s);
+cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, void *pk0, void *pk1, cudaStream_t s);
 /* strict: one launch per iteration, thread i owns row i and walks k ascending over QT */
 cudaError_t pqp_launch_gemv_strict_step(const pqp_gemv_args *a, const float *y_in, float *y_out, cudaStream_t s);
 /* evaluation of the status quantities for one y (any mode) */
