@@ -100,6 +100,10 @@ typedef struct pqp_opts {
 			       * 2 the batched loop on 3xTF32 instead (its truncating accumulator leaves it above the 1e-5 parity
 			       * tolerance after many updates: opt-in, for comparison) */
 	int l2_persist;    /* 1: pin as much of Q as the device allows in L2 (GEMV regime) default 1 */
+	int exploit_symmetry; /* FAST mode, one problem, fixed count: 1 (default) when the fp32 Qd of the handle is symmetric element
+			       * for element (tested once on the device) the loop reads its upper triangle only -- half the bytes per
+			       * update, same sums in a different order; 0 always read the full matrix.  Never applies to a Qd that is
+			       * not exactly symmetric */
 } pqp_opts;
 
 /* Per-problem result of a solve (replaces the printf's of PQP_CPU.c:741,1005-1006). */

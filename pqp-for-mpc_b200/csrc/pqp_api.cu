@@ -81,6 +81,7 @@ void pqp_default_opts(pqp_opts *o)
 	o->batch_capacity = 1;
 	o->use_tensor_cores = 1;
 	o->l2_persist = 1;
+	o->exploit_symmetry = 1;
 }
 
 int pqp_device_count(void)
@@ -476,7 +477,7 @@ static int ensure_sym(pqp_handle *h)
 	const int N = h->d.N, G = h->gemv_grid;
 	const char *e;
 	if ((e = getenv("PQP_GEMV_SYM")) && atoi(e) == 0) return PQP_OK;
-	if (h->o.order == PQP_ORDER_STRICT || G <= 0 || h->small_ok) return PQP_OK;
+	if (!h->o.exploit_symmetry || h->o.order == PQP_ORDER_STRICT || G <= 0 || h->small_ok) return PQP_OK;
 	const size_t budget = h->smem_optin > 1024 ? h->smem_optin - 1024 : 0;
 	pqp_sym_plan pl;
 	memset(&pl, 0, sizeof pl);

@@ -1,0 +1,112 @@
+"""GPU tests (-m gpu) of the upper-triangle loop (pqp_gemv_sym.cu): a single problem whose fp32 Qd is
+symmetric element for element is iterated from the strictly upper triangle alone (2N^2 bytes per update).  Same sums as
+updateY2 (PQP_CPU.c:603-618) in another order, so the bar is the FAST one of test_parity_gpu.py: the oracle on the same
+inputs, the tolerance rule of DESIGN.md 4, identical active sets; plus reproducibility, warm starts, ragged sizes, and the
+guarantee that a Qd which is NOT exactly symmetric never takes this path.
+"""
+import numpy as np
+import pytest
+
+from conftest import active_set, relerr
+from test_parity_gpu import TOL, check_fast
+
+pytestmark = pytest.mark.gpu
+
+
+def spd_dual(rng, N, rank):
+    """A symmetric positive semidefinite Qd = A A' with both signs off the diagonal, formed symmetric bit for bit."""
+    A = rng.standard_normal((N, rank)).astype(np.float32)
+    Q = (A.astype(np.float64) @ A.astype(np.float64).T).astype(np.float32)
+    Q = np.triu(Q) + np.triu(Q, 1).T
+    return np.ascontiguousarray(Q)
+
+
+@pytest.mark.parametrize("N,rank,K", [(2560, 3000, 40), (3001, 3500, 30), (2563, 700, 30)])
+def test_sym_against_the_oracle(pqp, oracle32, oracle64, N, rank, K):
+    """Well-conditioned (rank > N), ragged (N = 3001: not a multiple of 4, 24 tiles of which the last is partial) and
+    rank-deficient (rank < N) duals: STRICT is the oracle bit for bit, the upper-triangle loop meets the FAST tolerance."""
+    rng = np.random.default_rng(N)
+    Qd = spd_dual(rng, N, rank)
+    Fd = rng.uniform(-50, 50, N).astype(np.float32)
+    y32, th32 = oracle32.solve_fixed(Qd, Fd, K)
+    y64, _ = oracle64.solve_fixed(Qd, Fd, K)
+    with pqp.Solver(Qd=Qd, order=pqp.ORDER_STRICT) as s:
+        Ys, _, _ = s.solve(Fd=Fd, iters=K)
+        assert np.array_equal(Ys[0], y32)
+    with pqp.Solver(Qd=Qd) as s:
+        Y, _, st = s.solve(Fd=Fd, iters=K)
+        assert s.last_kernel.startswith("gemv_sym"), s.last_kernel
+        e = check_fast(Y[0], y32, y64, f"sym N={N}")
+        print(f"sym N={N}: errs (gpu-f32, gpu-f64, f32-f64) = {e}")
+        assert np.array_equal(active_set(Y[0]), active_set(y32))
+        assert st["iters"][0] == K and np.all(np.isfinite(Y)) and np.all(Y >= 0)
+        # reproducible bit for bit
+        Y2, _, _ = s.solve(Fd=Fd, iters=K)
+        assert np.array_equal(Y, Y2)
+    with pqp.Solver(Qd=Qd, exploit_symmetry=0) as s:
+        Yf, _, stf = s.solve(Fd=Fd, iters=K)
+        assert not s.last_kernel.startswith("gemv_sym"), s.last_kernel
+        check_fast(Yf[0], y32, y64, f"full N={N}")
+        assert relerr(Y[0], Yf[0]) <= max(TOL, 3 * relerr(y32, y64))
+        # the status block (evaluated by each kernel on its own g = Qd y + Fd) agrees between the two loops
+        for k in ("gap", "Jd", "kkt"):
+            np.testing.assert_allclose(st[k][0], stf[k][0], rtol=2e-3, err_msg=k)
+        assert abs(st["min_slack"][0] - stf["min_slack"][0]) <= 2e-3 * max(1.0, abs(stf["min_slack"][0]))
+
+
+def test_sym_generator_instance_warm_start_and_chunking(pqp):
+    """The reference generator's shape (testing/test_generator.c: Qp_inv diagonal, Gp in {0,+-1}, N = 4M): its Qd is symmetric
+    as computed.  K1 updates then K2 more from Y0 equals K1+K2 in one go, bit for bit; the primal comes back finite."""
+    prob, d = pqp.generate_testproblem(777, 640, 2560)
+    with pqp.Solver(d, prob) as s:
+        Ya, _, _ = s.solve(iters=70)
+        assert s.last_kernel.startswith("gemv_sym"), s.last_kernel
+        Yb, Ub, _ = s.solve(iters=50, Y0=Ya, primal=True)
+        Yc, Uc, stc = s.solve(iters=120, primal=True)
+        assert np.array_equal(Yb, Yc) and np.array_equal(Ub, Uc)
+        assert np.all(np.isfinite(Uc)) and stc["iters"][0] == 120
+    with pqp.Solver(d, prob, exploit_symmetry=0) as s:
+        Yf, _, _ = s.solve(iters=120)
+        assert not s.last_kernel.startswith("gemv_sym")
+        assert relerr(Yc[0], Yf[0]) <= 5e-5   # rank-deficient shape: the oracle's own fp32 noise is ~2e-5 here
+        assert np.array_equal(active_set(Yc[0], 1e-4), active_set(Yf[0], 1e-4))
+
+
+def test_sym_never_used_for_an_unsymmetric_dual(pqp):
+    """One element of the lower triangle off by one ulp: the handle must keep to the full-matrix loop, and give exactly what
+    it gives with the option switched off."""
+    rng = np.random.default_rng(9)
+    N = 2560
+    Qd = spd_dual(rng, N, 3000)
+    Qd[1700, 3] = np.nextafter(Qd[1700, 3], np.float32(np.inf))
+    Fd = rng.uniform(-50, 50, N).astype(np.float32)
+    with pqp.Solver(Qd=Qd) as s:
+        Y, _, _ = s.solve(Fd=Fd, iters=20)
+        k1 = s.last_kernel
+    with pqp.Solver(Qd=Qd, exploit_symmetry=0) as s:
+        Y0, _, _ = s.solve(Fd=Fd, iters=20)
+        k0 = s.last_kernel
+    assert not k1.startswith("gemv_sym") and k1 == k0
+    assert np.array_equal(Y, Y0)
+
+
+def test_sym_signed_zero_and_zero_rows(pqp, oracle32):
+    """-0.0 against +0.0 across the diagonal still counts as symmetric (their contributions are equal), and rows of Qd that are
+    entirely zero with Fd = 0 keep their duals at the initial value (example rows 14-27 behave like that)."""
+    rng = np.random.default_rng(10)
+    N = 2560
+    Qd = spd_dual(rng, N, 3000)
+    dead = [5, 1290, 2559]
+    for i in dead:
+        Qd[i, :] = 0.0
+        Qd[:, i] = 0.0
+    Qd[7, 900] = -0.0
+    Qd[900, 7] = 0.0
+    Fd = rng.uniform(-50, 50, N).astype(np.float32)
+    Fd[dead] = 0.0
+    y32, _ = oracle32.solve_fixed(Qd, Fd, 25)
+    with pqp.Solver(Qd=Qd) as s:
+        Y, _, _ = s.solve(Fd=Fd, iters=25)
+        assert s.last_kernel.startswith("gemv_sym"), s.last_kernel
+        assert np.all(Y[0][dead] == np.float32(1000.0))
+        assert relerr(Y[0], y32) <= TOL
