@@ -75,6 +75,13 @@ typedef struct pqp_host_problem {
 	const float *x;      /* [nState] the instance's own state (example/x.txt), optional */
 	const float *Z;      /* unused by the algorithm */
 	const float *Theta;  /* unused by the algorithm */
+	/* State-dependent constraint offsets (the reference never forms them): when non-NULL,
+	 *     Kp(x, D) = Kp + Kx*x + Kd*D        hence      Fd(x, D) = GQ*Fp(x, D) + Kp + Kx*x + Kd*D,
+	 * added after computeFd's sum (PQP_CPU.c:456-460) in the order written, k ascending.  NULL (the default, and what every
+	 * loader returns) is PQP_CPU.c's constant Kp.  pqp_output_offsets() builds them from Z / Theta.  They stay the caller's:
+	 * pqp_free_problem() leaves them alone. */
+	const float *Kx;     /* [N x nState] or NULL */
+	const float *Kd;     /* [N x nDisH]  or NULL */
 } pqp_host_problem;
 
 typedef enum pqp_order {
@@ -123,6 +130,15 @@ void pqp_default_opts(pqp_opts *o);
 /* M = pH*nInput, N = 4*pH*nInput, nDisH = nDis*pH  (PQP_CPU.c:940-941) */
 void pqp_dims_mpc(pqp_dims *d, int pHorizon, int nState, int nInput, int nOutput, int nDis);
 const char *pqp_strerror(int code);
+/*
+ * Kx [N x nState], Kd [N x nDisH] from the output maps the reference loads and never uses (Z [nOut x nState], Theta
+ * [nOut x nDisH], nOut = nOutput*pHorizon; PQP_CPU.c:889-911), read as the free response of the constrained outputs:
+ * out = Z*x + Theta*D + (output rows of Gp)*U.  With the row blocks of the example (N = 4M: U <= umax, -U <= -umin,
+ * out <= outmax, -out <= -outmin) the upper output bound moves by -(Z*x + Theta*D) and the lower by +(Z*x + Theta*D):
+ * rows [2M, 2M+nOut) of Kx, Kd are -Z, -Theta, rows [3M, 3M+nOut) are +Z, +Theta, all others zero.  Host-only helper;
+ * needs N == 4*M and nOut <= M.
+ */
+int pqp_output_offsets(const pqp_dims *d, const float *Z, const float *Theta, float *Kx, float *Kd);
 const char *pqp_last_cuda_error(void);
 /* number of usable sm_100 devices (0 without a GPU); never fails */
 int pqp_device_count(void);

@@ -45,7 +45,7 @@ _PROBLEM_PTRS = ("Qp_inv", "Gp", "Kp", "Fp1", "Fp2", "Fp3", "D", "Mp1", "Mp2", "
 
 
 class HostProblem(C.Structure):
-    _fields_ = ([(n, _FP) for n in _PROBLEM_PTRS] + [("Mp0", C.c_float)] + [(n, _FP) for n in ("x", "Z", "Theta")])
+    _fields_ = ([(n, _FP) for n in _PROBLEM_PTRS] + [("Mp0", C.c_float)] + [(n, _FP) for n in ("x", "Z", "Theta", "Kx", "Kd")])
 
 
 class Opts(C.Structure):
@@ -69,7 +69,7 @@ ABI_SYMBOLS = (
     "pqp_load_example", "pqp_load_testfile", "pqp_generate_testproblem", "pqp_write_testfile", "pqp_free_problem",
     "pqp_setup", "pqp_setup_dual", "pqp_destroy", "pqp_solve_batch", "pqp_solve_dual", "pqp_recover_primal",
     "pqp_solve_batch_primal", "pqp_get_dual", "pqp_get_linear_terms", "pqp_get_stream", "pqp_last_solve_ms",
-    "pqp_launch_count", "pqp_last_kernel", "pqp_device_qd", "pqp_matmul", "pqp_shift_duals",
+    "pqp_launch_count", "pqp_last_kernel", "pqp_device_qd", "pqp_matmul", "pqp_shift_duals", "pqp_output_offsets",
 )
 MM_STRICT, MM_SIMT, MM_TENSOR = 0, 1, 2
 
@@ -213,7 +213,7 @@ def write_testfile(path: str, prob: dict, d: Dims):
 
 def _numpy_to_problem(prob: dict):
     hp, keep = HostProblem(), []
-    for name in _PROBLEM_PTRS + ("x", "Z", "Theta"):
+    for name in _PROBLEM_PTRS + ("x", "Z", "Theta", "Kx", "Kd"):
         v = prob.get(name)
         if v is not None and np.size(v) > 0:
             a = np.ascontiguousarray(v, dtype=np.float32)
@@ -221,6 +221,18 @@ def _numpy_to_problem(prob: dict):
             setattr(hp, name, a.ctypes.data_as(_FP))
     hp.Mp0 = float(prob.get("Mp0", 0.0))
     return hp, keep
+
+
+def output_offsets(d: Dims, Z, Theta):
+    """pqp_output_offsets: (Kx [N x nState], Kd [N x nDisH]) for prob["Kx"], prob["Kd"] -- Kp(x, D) = Kp + Kx x + Kd D."""
+    Z = None if Z is None else np.ascontiguousarray(Z, dtype=np.float32)
+    Theta = None if Theta is None else np.ascontiguousarray(Theta, dtype=np.float32)
+    Kx = np.zeros((d.N, max(d.nState, 0)), np.float32)
+    Kd = np.zeros((d.N, max(d.nDisH, 0)), np.float32)
+    rc = lib().pqp_output_offsets(C.byref(d), _as_ptr(Z), _as_ptr(Theta), _as_ptr(Kx), _as_ptr(Kd))
+    if rc:
+        raise PQPError(rc, "pqp_output_offsets")
+    return Kx, Kd
 
 
 def _as_ptr(a):

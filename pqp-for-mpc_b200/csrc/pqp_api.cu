@@ -40,6 +40,7 @@ struct pqp_handle {
 	int have_primal, have_fp_model;
 	/* x-independent device data */
 	float *Q, *QT, *theta, *GQ, *Gp, *Qp_inv, *Kp, *Fp1, *Fp2, *Fp3, *Fp_const, *D;
+	float *Kx, *Kd; /* state / disturbance dependent part of Kp (NULL: constant Kp as in PQP_CPU.c) */
 	float *Mp1, *Mp2, *Mp3, *Mp4, *Mp5, *Mp6;
 	float Mp0;
 	float *QpT, *QnT; /* batched operands, built on first batched solve */
@@ -82,6 +83,32 @@ void pqp_default_opts(pqp_opts *o)
 	o->use_tensor_cores = 1;
 	o->l2_persist = 1;
 	o->exploit_symmetry = 1;
+}
+
+int pqp_output_offsets(const pqp_dims *d, const float *Z, const float *Theta, float *Kx, float *Kd)
+{
+	if (!d) return PQP_ERR_INVALID;
+	const int M = d->M, N = d->N, nS = d->nState, nd = d->nDisH, nOut = d->nOutput * d->pHorizon;
+	if (N != 4 * M || nOut < 0 || nOut > M) return PQP_ERR_INVALID;
+	if (Kx) {
+		if (!Z && nS > 0 && nOut > 0) return PQP_ERR_INVALID;
+		memset(Kx, 0, sizeof(float) * (size_t)N * nS);
+		for (int r = 0; r < nOut; r++)
+			for (int k = 0; k < nS; k++) {
+				Kx[(size_t)(2 * M + r) * nS + k] = -Z[(size_t)r * nS + k];
+				Kx[(size_t)(3 * M + r) * nS + k] = Z[(size_t)r * nS + k];
+			}
+	}
+	if (Kd) {
+		if (!Theta && nd > 0 && nOut > 0) return PQP_ERR_INVALID;
+		memset(Kd, 0, sizeof(float) * (size_t)N * nd);
+		for (int r = 0; r < nOut; r++)
+			for (int k = 0; k < nd; k++) {
+				Kd[(size_t)(2 * M + r) * nd + k] = -Theta[(size_t)r * nd + k];
+				Kd[(size_t)(3 * M + r) * nd + k] = Theta[(size_t)r * nd + k];
+			}
+	}
+	return PQP_OK;
 }
 
 int pqp_device_count(void)
@@ -368,6 +395,8 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 	}
 #undef UP
 	if (nS == 0 && (rc = upload(h, &h->Fp_const, p->Fp, M))) { pqp_destroy(h); return rc; }
+	if (p->Kx && nS > 0 && (rc = upload(h, &h->Kx, p->Kx, (size_t)N * nS))) { pqp_destroy(h); return rc; }
+	if (p->Kd && nd > 0 && (rc = upload(h, &h->Kd, p->Kd, (size_t)N * nd))) { pqp_destroy(h); return rc; }
 
 	const int strict = o.order == PQP_ORDER_STRICT;
 	if ((rc = dalloc(&h->GQ, (size_t)N * M)) || (rc = dalloc(&h->Q, (size_t)N * h->ldq))) { pqp_destroy(h); return rc; }
@@ -452,7 +481,7 @@ void pqp_destroy(pqp_handle *h)
 		if (h->l2_window_set) l2_persist_window(h, 0);
 	}
 	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
-			 h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
+			 h->Kx, h->Kd, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
 			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf, h->pk0, h->pk1,
 			 h->sym.units, h->sym.cta_u0, h->sym.cta_j0, h->sym.strip_c0, h->sym.strip_c1, h->sym.rowpart, h->sym.colpart };
 	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
@@ -812,6 +841,10 @@ static int form_linear_terms(pqp_handle *h, const float *X, const float *D, int 
 	CK(pqp_launch_fp(h->Fp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, Dd, Dstride, h->X, B, M, nd, nS, h->stream));
 	CK(pqp_launch_fd(h->Fd, h->GQ, h->Fp, h->Kp, B, N, M, strict, h->stream));
 	h->launches += 2;
+	if (h->Kx || h->Kd) { /* Kp(x, D) = Kp + Kx*x + Kd*D */
+		CK(pqp_launch_fd_offsets(h->Fd, h->Kx, h->X, nS, h->Kd, Dd, Dstride, nd, B, N, h->stream));
+		h->launches++;
+	}
 	h->fp_B = B;
 	if (want_status) {
 		CK(pqp_launch_md(h->Md, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, Dd, Dstride, h->X, B, M,

@@ -41,6 +41,9 @@ cudaError_t pqp_launch_fp(float *Fp, const float *Fp1, const float *Fp2, const f
 /* Fd[b] = GQ*Fp[b] + Kp (computeFd, PQP_CPU.c:456-460); strict: k ascending per thread */
 cudaError_t pqp_launch_fd(float *Fd, const float *GQ, const float *Fp, const float *Kp, int B, int N, int M,
 			  int strict, cudaStream_t s);
+/* Fd[b] += Kx*X[b] + Kd*D[b] (state-dependent constraint offsets; either matrix may be NULL); k ascending, separately rounded */
+cudaError_t pqp_launch_fd_offsets(float *Fd, const float *Kx, const float *X, int nState, const float *Kd, const float *D, int D_stride,
+				  int nd, int B, int N, cudaStream_t s);
 /* Md[b] = Fp' Qp_inv Fp - Mp(x_b) (computeMd PQP_CPU.c:472-479, computeMp :395-428); Mp1==NULL: Mp = Mp0 */
 cudaError_t pqp_launch_md(float *Md, const float *Fp, const float *Qp_inv, const float *Mp1, const float *Mp2,
 			  const float *Mp3, const float *Mp4, const float *Mp5, const float *Mp6, float Mp0,

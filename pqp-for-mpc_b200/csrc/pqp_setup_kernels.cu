@@ -484,3 +484,35 @@ cudaError_t pqp_launch_shift_duals(float *out, const float *in, int B, int pH, i
 	shift_duals_kernel<<<(unsigned)blocks, 256, 0, s>>>(out, in, B, pH, nI, y_floor);
 	return cudaGetLastError();
 }
+
+/* ---- state-dependent constraint offsets: Fd[b][i] += sum_k Kx[i][k] x_b[k] + sum_k Kd[i][k] D_b[k] -------------- */
+__global__ void fd_offsets_kernel(float *Fd, const float *Kx, const float *X, int nS, const float *Kd, const float *D, int D_stride, int nd,
+				  int B, int N)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+	if (i >= N || b >= B) return;
+	float acc = Fd[(size_t)b * N + i];
+	if (Kx) {
+		float t = 0.0f;
+		for (int k = 0; k < nS; k++) t = __fadd_rn(t, __fmul_rn(Kx[(size_t)i * nS + k], X[(size_t)b * nS + k]));
+		acc = __fadd_rn(acc, t);
+	}
+	if (Kd) {
+		float t = 0.0f;
+		for (int k = 0; k < nd; k++) t = __fadd_rn(t, __fmul_rn(Kd[(size_t)i * nd + k], D[(size_t)b * D_stride + k]));
+		acc = __fadd_rn(acc, t);
+	}
+	Fd[(size_t)b * N + i] = acc;
+}
+
+cudaError_t pqp_launch_fd_offsets(float *Fd, const float *Kx, const float *X, int nState, const float *Kd, const float *D, int D_stride,
+				  int nd, int B, int N, cudaStream_t s)
+{
+	if (B <= 0 || N <= 0) return cudaSuccess;
+	for (int b0 = 0; b0 < B; b0 += 65535) { /* gridDim.y limit */
+		const int nb = B - b0 < 65535 ? B - b0 : 65535;
+		fd_offsets_kernel<<<dim3((N + 127) / 128, nb), 128, 0, s>>>(Fd + (size_t)b0 * N, Kx, X ? X + (size_t)b0 * nState : X, nState, Kd,
+									    D ? D + (size_t)b0 * D_stride : D, D_stride, nd, nb, N);
+	}
+	return cudaGetLastError();
+}

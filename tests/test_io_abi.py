@@ -36,6 +36,22 @@ def test_struct_layouts_match_header(pqp):
     assert C.sizeof(pqp.Status) == pqp.STATUS_DTYPE.itemsize == 24
 
 
+def test_output_offsets_helper(pqp):
+    """pqp_output_offsets (host only): Kx = [0; 0; -Z; +Z], Kd = [0; 0; -Theta; +Theta] on the example's row blocks, and the
+    shapes it must refuse."""
+    prob, d = pqp.load_example(EXAMPLE_DIR)
+    M, N, nO = d.M, d.N, d.nOutput * d.pHorizon
+    Kx, Kd = pqp.output_offsets(d, prob["Z"], prob["Theta"])
+    assert Kx.shape == (N, d.nState) and Kd.shape == (N, d.nDisH)
+    Z, Th = prob["Z"].reshape(nO, d.nState), prob["Theta"].reshape(nO, d.nDisH)
+    assert np.array_equal(Kx[2 * M:2 * M + nO], -Z) and np.array_equal(Kx[3 * M:3 * M + nO], Z)
+    assert np.array_equal(Kd[2 * M:2 * M + nO], -Th) and np.array_equal(Kd[3 * M:3 * M + nO], Th)
+    assert not Kx[:2 * M].any() and not Kd[:2 * M].any()
+    bad = pqp.dims_plain(d.M, d.N + 1)
+    with pytest.raises(pqp.PQPError):
+        pqp.output_offsets(bad, prob["Z"], prob["Theta"])
+
+
 def test_example_loader_matches_oracle_loader(pqp, oracle32):
     got, d = pqp.load_example(EXAMPLE_DIR)
     want = oracle32.load_example(EXAMPLE_DIR)

@@ -354,3 +354,59 @@ def test_c3_full_size_fast_against_strict(pqp):
             assert np.all(Y >= 0) and np.all(np.isfinite(Y)) and np.all(np.isfinite(U))
             Y2, _, st2 = s.solve(iters=400)
             assert st2["kkt"][0] <= st["kkt"][0] * 1.001
+
+
+# ------------------------------------------------------------------------------------------------
+# state-dependent constraint offsets Kp(x, D) = Kp + Kx x + Kd D (the reference loads Z / Theta and never uses them)
+# ------------------------------------------------------------------------------------------------
+def test_state_dependent_constraint_offsets(pqp, oracle32, oracle64):
+    """With Kx / Kd the linear term is Fd(x, D) = GQ Fp(x, D) + Kp + Kx x + Kd D: checked against numpy on the handle's own
+    Fd without them, then the loop on that Fd against the oracle (STRICT bit for bit, FAST within tolerance), single problem
+    and a batch of states that each move their own bounds."""
+    prob, d = pqp.load_example(EXAMPLE_DIR)
+    Kx, Kd = pqp.output_offsets(d, prob["Z"], prob["Theta"])
+    rng = np.random.default_rng(3)
+    B = 40
+    X = (prob["x"][None, :] + rng.standard_normal((B, d.nState)).astype(np.float32)).astype(np.float32)
+    with pqp.Solver(d, prob, order=pqp.ORDER_STRICT) as s:
+        s.solve(X, iters=1)
+        Fd0, _ = s.linear_terms(B)
+        Qd, _, _ = s.dual()
+    pk = dict(prob, Kx=Kx, Kd=Kd)
+    # expected offsets, in the kernel's order (k ascending, separately rounded), then added to Fd in fp32
+    def seq(Mat, v):
+        t = np.zeros(Mat.shape[0], np.float32)
+        for k in range(Mat.shape[1]):
+            t = (t + (Mat[:, k] * np.float32(v[k])).astype(np.float32)).astype(np.float32)
+        return t
+    Dv = prob["D"].astype(np.float32)
+    want = np.stack([((Fd0[b] + seq(Kx, X[b])).astype(np.float32) + seq(Kd, Dv)).astype(np.float32) for b in range(B)])
+    assert np.abs(want - Fd0).max() > 1.0            # the offsets really move the output rows
+    assert np.array_equal(want[:, :2 * d.M], Fd0[:, :2 * d.M])   # and only those
+    for order in (pqp.ORDER_STRICT, pqp.ORDER_FAST):
+        with pqp.Solver(d, pk, order=order) as s:
+            Y1, U1, st1 = s.solve(X[:1], iters=200, primal=True)
+            Fd1, _ = s.linear_terms(1)
+            assert np.array_equal(Fd1[0], want[0])
+            y32, _ = oracle32.solve_fixed(Qd, want[0], 200)
+            y64, _ = oracle64.solve_fixed(Qd, want[0], 200)
+            if order == pqp.ORDER_STRICT:
+                assert np.array_equal(Y1[0], y32)
+            else:
+                check_fast(Y1[0], y32, y64, "offsets, single")
+            YB, UB, _ = s.solve(X, iters=200, primal=True)
+            FdB, _ = s.linear_terms(B)
+            assert np.array_equal(FdB, want)
+            for b in (0, 7, B - 1):
+                yb32, _ = oracle32.solve_fixed(Qd, want[b], 200)
+                yb64, _ = oracle64.solve_fixed(Qd, want[b], 200)
+                if order == pqp.ORDER_STRICT:
+                    assert np.array_equal(YB[b], yb32), b
+                else:
+                    check_fast(YB[b], yb32, yb64, f"offsets, batch {b}")
+            assert np.all(np.isfinite(UB))
+    # without Kx / Kd nothing changed: PQP_CPU.c's constant Kp
+    with pqp.Solver(d, prob, order=pqp.ORDER_STRICT) as s:
+        s.solve(X, iters=1)
+        Fd2, _ = s.linear_terms(B)
+        assert np.array_equal(Fd2, Fd0)
