@@ -497,7 +497,7 @@ void pqp_destroy(pqp_handle *h)
 
 /*
  * The upper-triangle loop (pqp_gemv_sym.cu) needs Qd symmetric element for element; examined once per handle, on the
- * first single-problem fixed-count solve that could use it.  Returns PQP_OK with h->sym_state set to 1 or -1.
+ * first single-problem solve that could use it.  Returns PQP_OK with h->sym_state set to 1 or -1.
  */
 static int ensure_sym(pqp_handle *h)
 {
@@ -647,11 +647,13 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		*y_res = h->ybuf1;
 		return PQP_OK;
 	}
-	if (iters > 0) {
+	if (!(iters <= 0 && getenv("PQP_GEMV_SYM_TOL") && atoi(getenv("PQP_GEMV_SYM_TOL")) == 0)) {
+		/* fixed count, or run to tolerance with the stop test evaluated by the owners every check_every updates */
 		int rc = ensure_sym(h);
 		if (rc) return rc;
 		if (h->sym_state == 1) {
-			h->last_kernel = h->sym.resident >= (h->sym.U + h->gemv_grid - 1) / h->gemv_grid ? "gemv_sym_resident" : "gemv_sym_stream";
+			const int all_res = h->sym.resident >= (h->sym.U + h->gemv_grid - 1) / h->gemv_grid;
+			h->last_kernel = iters > 0 ? (all_res ? "gemv_sym_resident" : "gemv_sym_stream") : (all_res ? "gemv_sym_resident_tol" : "gemv_sym_stream_tol");
 			CK(pqp_launch_gemv_sym(&a, &h->sym, h->pk0, h->pk1, h->stream));
 			h->launches++;
 			*y_res = h->ybuf1;

@@ -49,6 +49,7 @@
 #define SY_WARPS 8
 #define SY_THREADS SY_CONS
 #define SY_FLUSH_COST 1.7
+#define SY_RC 6                     /* per owned row: theta+q-, theta+q+, Fd, slack tolerance, y, previous y */
 #define SY_D 4                      /* units in flight per warp (cp.async groups) */
 #define SY_TPR 4                    /* threads per owned row in the owner phase (64 rows per round) */
 #define SY_OB 18                    /* packets in flight per owner thread */
@@ -209,7 +210,7 @@ struct SymGeom {
 };
 
 /*
- * Shared memory: ring [SY_D][SY_UNIT] | resident [R][SY_UNIT] | y [nb*128] | scr [2][8][128] float2 | osum [4][64] float2 | rowc [rows_max][5] | red [8*8]
+ * Shared memory: ring [SY_D][SY_UNIT] | resident [R][SY_UNIT] | y [nb*128] | scr [2][8][128] float2 | osum [4][64] float2 | rowc [rows_max][6] | red [8*8]
  *
  * Lane mapping inside a unit (64 rows x 128 columns): warp w owns rows 8w..8w+7; lane (a = lane>>3, b = lane&7) owns rows
  * 8w+a and 8w+4+a and columns 16b..16b+15 -- eight float4 per unit, stored lane-major so every shared-memory access is
@@ -218,8 +219,16 @@ struct SymGeom {
  * block-wide synchronisation in the unit loop at all.  Row sums need three shuffle rounds over b; the sixteen column sums of a
  * lane stay in its registers for the whole strip (reduced over a and over the warps only when the strip changes).
  */
-__global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_args a, const SymGeom g)
+/*
+ * TOL (run to tolerance, iters <= 0): every check_every passes the owners also form the stop-test terms of terminate()
+ * (PQP_CPU.c:673-687, on g = Qd y + Fd) for y_p and publish them as three 16-byte packets per CTA; y_{p+1} is published as
+ * always and the decision is read by every CTA at the start of the NEXT pass, all folding the 148 x 3 values in the same
+ * order, so all decide alike.  A converged run leaves with y_p (each owner keeps the previous value of its rows): bit for bit
+ * what the fixed-count solve returns at the reported count.
+ */
+template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_args a, const SymGeom g)
 {
+	__shared__ float chk_s[TOL ? 160 : 1][6];
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 	const int N = a.N, nb = g.nb;
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 	float2 *scr = reinterpret_cast<float2 *>(y_s + (size_t)nb * SY_BS); /* [2][8][128] column sums of the warps */
 	float2 *osum = scr + 2 * SY_WARPS * SY_BS; /* [SY_TPR][64] partial sums of the owner phase */
 	float *rowc = reinterpret_cast<float *>(osum + SY_CONS);
-	float *red = rowc + 5 * (size_t)g.rows_max;
+	float *red = rowc + SY_RC * (size_t)g.rows_max;
 	int *tab_c0 = reinterpret_cast<int *>(red + SY_WARPS * 8); /* strip_c0 [nb], strip_c1 [nb], cta_j0 [G]: the owner phase reads them every pass */
 	int *tab_c1 = tab_c0 + nb;
 	int *tab_j0 = tab_c1 + nb;
@@ -246,7 +255,9 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 	 * the next y: the ping-pong packet buffers stay safe without a global barrier (a CTA polling rows it does not feed could be
 	 * overtaken by two passes and spin on an epoch that is gone).  The y of its OWN rows never leaves the CTA (rowc[5*rr+4]). */
 
-	const int passes = a.iters + 1; /* iters updates + one evaluation pass */
+	const int passes = (TOL ? a.max_iters : a.iters) + 1; /* updates + one evaluation pass */
+	uint4 *cpk4 = reinterpret_cast<uint4 *>(a.partials); /* TOL: [2][G][3] check packets */
+	float *fin = a.partials + (TOL ? (size_t)2 * G * 12 : 0); /* final per-CTA slots, clear of the check packets */
 
 	/* ---- this warp's copy pipeline ---- */
 	const int T = nU - R; /* streamed units per pass */
@@ -298,11 +309,11 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 	for (int rr = tid; rr < nrows; rr += SY_CONS) {
 		const int i = r0 + rr;
 		const float th = a.theta[i], qii = a.Q[(size_t)i * a.ldq + i];
-		rowc[5 * rr + 0] = th + fmaxf(-qii, 0.0f);
-		rowc[5 * rr + 1] = th + fmaxf(qii, 0.0f);
-		rowc[5 * rr + 2] = a.Fd[i];
-		rowc[5 * rr + 3] = a.Kp ? fmaxf(a.erc * a.Kp[i], a.eac) : a.eac;
-		rowc[5 * rr + 4] = __ldcg(a.ybuf0 + i); /* y of the rows this CTA owns */
+		rowc[SY_RC * rr + 0] = th + fmaxf(-qii, 0.0f);
+		rowc[SY_RC * rr + 1] = th + fmaxf(qii, 0.0f);
+		rowc[SY_RC * rr + 2] = a.Fd[i];
+		rowc[SY_RC * rr + 3] = a.Kp ? fmaxf(a.erc * a.Kp[i], a.eac) : a.eac;
+		rowc[SY_RC * rr + 4] = __ldcg(a.ybuf0 + i); /* y of the rows this CTA owns */
 	}
 	for (int i = N + tid; i < nb * SY_BS; i += SY_CONS) y_s[i] = 0.0f; /* the padding of Q is zero; keep 0 * y finite */
 	const int Jstart = g.cta_j0[cta];
@@ -338,8 +349,11 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 	unsigned bar_target = 0, flushes = 0;
 	float e_min = INFINITY, e_gap = 0.0f, e_jd = 0.0f, e_kkt = 0.0f, e_viol = -INFINITY;
 
+	int next_chk = 0;     /* TOL: check passes at p = 0, check_every, 2*check_every, ... */
+	bool pending = false; /* TOL: the previous pass published a check; decide before this pass's units */
 	for (int p = 0; p < passes; p++) {
 		const bool is_last = (p == passes - 1);
+		const bool chk = TOL && !is_last && p == next_chk;
 		const uint2 *pk_in = (p & 1) ? g.pk1 : g.pk0;
 		uint2 *pk_out = (p & 1) ? g.pk0 : g.pk1;
 		const uint32_t ep = (uint32_t)p + 1u; /* epoch of this pass's partial packets */
@@ -348,6 +362,20 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 
 		long long tA = 0, tB = 0, tC = 0;
 		if (g.prof) tA = clock64();
+		if (TOL && pending) {
+			/* the stop test of pass p-1: one 16-byte polling load per packet; published before that pass's y, so it is there */
+			const unsigned cq = (unsigned)((p - 1) / a.check_every) + 1u;
+			for (int x = tid; x < 3 * (int)G; x += SY_CONS) {
+				const uint4 *src = cpk4 + (size_t)(cq & 1u) * G * 3 + x;
+				uint4 v = ld_pair_raw(src);
+				while (v.y != cq || v.w != cq) {
+					__nanosleep(20);
+					v = ld_pair_raw(src);
+				}
+				chk_s[x / 3][2 * (x % 3)] = __uint_as_float(v.x);
+				chk_s[x / 3][2 * (x % 3) + 1] = __uint_as_float(v.z);
+			}
+		}
 		/* ---- y of this pass -> shared memory ---- */
 		if (p == 0) {
 			for (int i = tid; i < N; i += SY_CONS) y_s[i] = __ldcg(a.ybuf0 + i);
@@ -396,6 +424,34 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 				for (int i = 4 * n4 + tid; i < N; i += SY_CONS) y_s[i] = ld_packet(pk_in + i, (uint32_t)p);
 		}
 		consumer_sync();
+		if (TOL && pending) {
+			/* every warp of every CTA folds all CTAs' values in the same order: one decision for the whole grid */
+			float v_min = INFINITY, v_gap = 0.0f, v_jd = 0.0f, v_kkt = 0.0f, v_viol = -INFINITY;
+			for (unsigned c = lane; c < G; c += 32) {
+				v_min = fminf(v_min, chk_s[c][0]); v_gap += chk_s[c][1]; v_jd += chk_s[c][2]; v_kkt = fmaxf(v_kkt, chk_s[c][3]);
+				v_viol = fmaxf(v_viol, chk_s[c][4]);
+			}
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				v_min = fminf(v_min, __shfl_xor_sync(0xffffffffu, v_min, o));
+				v_gap += __shfl_xor_sync(0xffffffffu, v_gap, o);
+				v_jd += __shfl_xor_sync(0xffffffffu, v_jd, o);
+				v_kkt = fmaxf(v_kkt, __shfl_xor_sync(0xffffffffu, v_kkt, o));
+				v_viol = fmaxf(v_viol, __shfl_xor_sync(0xffffffffu, v_viol, o));
+			}
+			const float Jd = v_jd + (a.Md ? 0.5f * a.Md[0] : 0.0f);
+			if (v_viol <= 0.0f && fabsf(v_gap) <= a.eaj && fabsf(v_gap) <= a.erj * fabsf(Jd)) {
+				/* converged at y_{p-1}: every owner still holds it */
+				for (int rr = tid; rr < nrows; rr += SY_CONS) a.ybuf1[r0 + rr] = rowc[SY_RC * rr + 5];
+				if (cta == 0 && tid == 0) {
+					pqp_status o;
+					o.iters = p - 1; o.converged = 1; o.min_slack = v_min; o.gap = v_gap; o.Jd = Jd; o.kkt = v_kkt;
+					*a.status = o;
+					*a.result_buf = 1;
+				}
+				break; /* uniform across the grid */
+			}
+		}
 		if (g.prof) tB = clock64();
 
 		/* ---- the units of this CTA ---- */
@@ -590,21 +646,24 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 			if (gb + SY_CONS / SY_TPR < nrows) consumer_sync(); /* osum is reused by the next round */
 			if (valid && k == 0) {
 				const int i = r0 + rr;
-				const float y_mine = rowc[5 * rr + 4], fd_r = rowc[5 * rr + 2];
-				num = fmaf(rowc[5 * rr + 0], y_mine, num) + fmaxf(-fd_r, 0.0f);
-				den = fmaf(rowc[5 * rr + 1], y_mine, den) + fmaxf(fd_r, 0.0f);
+				const float y_mine = rowc[SY_RC * rr + 4], fd_r = rowc[SY_RC * rr + 2];
+				num = fmaf(rowc[SY_RC * rr + 0], y_mine, num) + fmaxf(-fd_r, 0.0f);
+				den = fmaf(rowc[SY_RC * rr + 1], y_mine, den) + fmaxf(fd_r, 0.0f);
 				if (!is_last) {
 					const float yn = __fdiv_rn(num, den) * y_mine;
 					st_packet(pk_out + i, yn, (uint32_t)(p + 1));
-					rowc[5 * rr + 4] = yn;
+					rowc[SY_RC * rr + 4] = yn;
+					if (TOL) rowc[SY_RC * rr + 5] = y_mine;
 				} else {
 					a.ybuf1[i] = y_mine; /* the answer, as a plain vector */
+				}
+				if (is_last || chk) {
 					const float gq = den - num;
 					e_min = fminf(e_min, gq);
 					e_gap += y_mine * gq;
 					e_jd += y_mine * (0.5f * (gq + fd_r));
 					e_kkt = fmaxf(e_kkt, fabsf(fminf(y_mine, gq)));
-					e_viol = fmaxf(e_viol, -gq - rowc[5 * rr + 3]);
+					e_viol = fmaxf(e_viol, -gq - rowc[SY_RC * rr + 3]);
 				}
 			}
 		}
@@ -615,7 +674,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 			g.prof[cta * 4 + 1] += tC - tB;
 			g.prof[cta * 4 + 2] += tD - tC;
 		}
-		if (is_last) {
+		if (is_last || chk) {
 #pragma unroll
 			for (int o = 16; o; o >>= 1) {
 				e_min = fminf(e_min, __shfl_xor_sync(0xffffffffu, e_min, o));
@@ -634,14 +693,26 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 					e_min = fminf(e_min, red[w * 8 + 0]); e_gap += red[w * 8 + 1]; e_jd += red[w * 8 + 2];
 					e_kkt = fmaxf(e_kkt, red[w * 8 + 3]); e_viol = fmaxf(e_viol, red[w * 8 + 4]);
 				}
-				float *slot = a.partials + (size_t)cta * 8;
-				slot[0] = e_min; slot[1] = e_gap; slot[2] = e_jd; slot[3] = e_kkt; slot[4] = e_viol;
+				if (is_last) {
+					float *slot = fin + (size_t)cta * 8;
+					slot[0] = e_min; slot[1] = e_gap; slot[2] = e_jd; slot[3] = e_kkt; slot[4] = e_viol;
+				} else {
+					/* this CTA's share of the stop test on y_p, epoch = number of the check; read at the start of the next pass */
+					const unsigned cq = (unsigned)(p / a.check_every) + 1u;
+					uint4 *mine_c = cpk4 + ((size_t)(cq & 1u) * G + cta) * 3;
+					st_pair(mine_c + 0, e_min, e_gap, cq);
+					st_pair(mine_c + 1, e_jd, e_kkt, cq);
+					st_pair(mine_c + 2, e_viol, 0.0f, cq);
+				}
 			}
+			e_min = INFINITY; e_gap = 0.0f; e_jd = 0.0f; e_kkt = 0.0f; e_viol = -INFINITY;
+		}
+		if (is_last) {
 			grid_barrier_consumers(a.barrier, bar_target, G);
 			if (cta == 0 && warp == 0) {
 				float v_min = INFINITY, v_gap = 0.0f, v_jd = 0.0f, v_kkt = 0.0f;
 				for (unsigned c = lane; c < G; c += 32) {
-					const float *sl = a.partials + (size_t)c * 8;
+					const float *sl = fin + (size_t)c * 8;
 					v_min = fminf(v_min, __ldcg(sl + 0)); v_gap += __ldcg(sl + 1); v_jd += __ldcg(sl + 2);
 					v_kkt = fmaxf(v_kkt, __ldcg(sl + 3));
 				}
@@ -654,7 +725,7 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 				}
 				if (lane == 0) {
 					pqp_status o;
-					o.iters = a.iters;
+					o.iters = p; /* TOL: the cap; a converged run left at the decision above */
 					o.converged = 0;
 					o.min_slack = v_min;
 					o.gap = v_gap;
@@ -666,6 +737,10 @@ __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_
 			}
 		} else {
 			consumer_sync(); /* y_s is rewritten by the next pass */
+		}
+		if (TOL) {
+			pending = chk;
+			if (chk) next_chk += a.check_every;
 		}
 	}
 	cp_async_wait<0>();
@@ -789,7 +864,7 @@ int pqp_gemv_sym_tables(int N, int G, int *cta_u0, int *cta_j0, int *strip_c0, i
 
 static size_t sym_smem_bytes(int nb, int rows_max, int resident)
 {
-	return sizeof(float) * ((size_t)(SY_D + resident) * SY_UNIT + (size_t)nb * SY_BS + 4 * SY_WARPS * SY_BS + 2 * SY_CONS + 5 * (size_t)rows_max +
+	return sizeof(float) * ((size_t)(SY_D + resident) * SY_UNIT + (size_t)nb * SY_BS + 4 * SY_WARPS * SY_BS + 2 * SY_CONS + SY_RC * (size_t)rows_max +
 				SY_WARPS * 8) + sizeof(int) * (3 * (size_t)nb + 1 + 512) + 128; /* + the tables (grid <= 512) */
 }
 
@@ -842,11 +917,14 @@ cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, 
 	if (e == cudaSuccess) e = cudaMemsetAsync(a->barrier, 0, sizeof(unsigned), s);
 	if (e != cudaSuccess) return e;
 	const size_t smem = sym_smem_bytes(g.nb, g.rows_max, g.resident);
-	e = cudaFuncSetAttribute((const void *)gemv_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	const void *fn = a->iters > 0 ? (const void *)gemv_sym_kernel<false> : (const void *)gemv_sym_kernel<true>;
+	if (a->iters <= 0) e = cudaMemsetAsync(a->partials, 0, (size_t)2 * a->grid * 3 * sizeof(uint4), s); /* check packets: epoch 0 = none */
+	if (e != cudaSuccess) return e;
+	e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	pqp_gemv_args args = *a;
 	void *params[] = { (void *)&args, (void *)&g };
-	e = cudaLaunchCooperativeKernel((const void *)gemv_sym_kernel, dim3(a->grid), dim3(SY_THREADS), params, smem, s);
+	e = cudaLaunchCooperativeKernel(fn, dim3(a->grid), dim3(SY_THREADS), params, smem, s);
 	if (prof && e == cudaSuccess) {
 		long long hp[4 * 256];
 		cudaStreamSynchronize(s);
@@ -854,15 +932,15 @@ cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, 
 		double sum[3] = { 0, 0, 0 }, mx[3] = { 0, 0, 0 }, mn[3] = { 1e30, 1e30, 1e30 };
 		for (int c = 0; c < a->grid; c++)
 			for (int k = 0; k < 3; k++) {
-				const double v = (double)hp[c * 4 + k] / (double)a->iters;
+				const double v = (double)hp[c * 4 + k] / (double)(a->iters > 0 ? a->iters : 1);
 				sum[k] += v;
 				if (v > mx[k]) mx[k] = v;
 				if (v < mn[k]) mn[k] = v;
 			}
 		if (atoi(getenv("PQP_SYM_PROF")) > 1)
 			for (int c = 0; c < a->grid; c++)
-				fprintf(stderr, "cta %3d: y %6.0f units %6.0f owner %6.0f\n", c, (double)hp[c * 4] / a->iters, (double)hp[c * 4 + 1] / a->iters,
-					(double)hp[c * 4 + 2] / a->iters);
+				fprintf(stderr, "cta %3d: y %6.0f units %6.0f owner %6.0f\n", c, (double)hp[c * 4] / (a->iters > 0 ? a->iters : 1), (double)hp[c * 4 + 1] / (a->iters > 0 ? a->iters : 1),
+					(double)hp[c * 4 + 2] / (a->iters > 0 ? a->iters : 1));
 		fprintf(stderr, "pqp: gemv_sym cycles per pass (min/mean/max over CTAs): y fetch %.0f/%.0f/%.0f  units %.0f/%.0f/%.0f  owner %.0f/%.0f/%.0f\n",
 			mn[0], sum[0] / a->grid, mx[0], mn[1], sum[1] / a->grid, mx[1], mn[2], sum[2] / a->grid, mx[2]);
 	}

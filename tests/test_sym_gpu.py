@@ -110,3 +110,42 @@ def test_sym_signed_zero_and_zero_rows(pqp, oracle32):
         assert s.last_kernel.startswith("gemv_sym"), s.last_kernel
         assert np.all(Y[0][dead] == np.float32(1000.0))
         assert relerr(Y[0], y32) <= TOL
+
+
+def test_sym_run_to_tolerance(pqp):
+    """iters <= 0 on the upper-triangle loop: the owners form the stop test of terminate() (PQP_CPU.c:673-687, on g = Qd y + Fd)
+    every check_every updates; the run stops at a check, bit-identical to the fixed-count solve at the reported count, at the
+    same place (to within a few checks: the sums are ordered differently) as the full-matrix tolerance kernel; a cap that is
+    too small reports exactly max_iters updates, unconverged."""
+    rng = np.random.default_rng(21)
+    N = 2560
+    Qd = spd_dual(rng, N, 3000) / np.float32(3000.0)
+    Qd[np.arange(N), np.arange(N)] += np.float32(0.5)     # well conditioned: converges in a few hundred updates
+    Fd = rng.uniform(-50, 50, N).astype(np.float32)
+    opts = dict(eaj=1e30, erj=1e-5, eac=1e-3, erc=1e-3, check_every=8, max_iters=20000)
+    with pqp.Solver(Qd=Qd, **opts) as s:
+        Y, _, st = s.solve(Fd=Fd, iters=0)
+        assert s.last_kernel.startswith("gemv_sym") and s.last_kernel.endswith("_tol"), s.last_kernel
+        it = int(st["iters"][0])
+        print("sym run-to-tolerance:", it, "updates, gap", st["gap"][0], "min_slack", st["min_slack"][0])
+        assert st["converged"][0] == 1 and 0 < it < 20000 and it % 8 == 0
+        assert st["min_slack"][0] >= -1e-3 and abs(st["gap"][0]) <= 1e-5 * abs(st["Jd"][0])
+        Yf, _, stf = s.solve(Fd=Fd, iters=it)
+        assert s.last_kernel.startswith("gemv_sym") and not s.last_kernel.endswith("_tol")
+        assert np.array_equal(Y, Yf)
+        np.testing.assert_allclose(st["gap"][0], stf["gap"][0], rtol=1e-6)
+        # the previous check had not passed yet
+        if it >= 8:
+            _, _, stp = s.solve(Fd=Fd, iters=it - 8)
+            assert not (stp["min_slack"][0] >= -1e-3 and abs(stp["gap"][0]) <= 1e-5 * abs(stp["Jd"][0]))
+    with pqp.Solver(Qd=Qd, exploit_symmetry=0, **opts) as s:
+        Y0, _, st0 = s.solve(Fd=Fd, iters=0)
+        assert not s.last_kernel.startswith("gemv_sym")
+        # the criterion is crossed slowly at the tail, and the two loops round differently: the counts agree to a few checks
+        assert st0["converged"][0] == 1 and abs(int(st0["iters"][0]) - it) <= max(8, 0.02 * it)
+        assert relerr(Y[0], Y0[0]) <= 1e-4
+    with pqp.Solver(Qd=Qd, **dict(opts, max_iters=40)) as s:
+        Yc, _, stc = s.solve(Fd=Fd, iters=0)
+        assert stc["converged"][0] == 0 and stc["iters"][0] == 40
+        Yd, _, _ = s.solve(Fd=Fd, iters=40)
+        assert np.array_equal(Yc, Yd)
