@@ -149,3 +149,28 @@ def test_sym_run_to_tolerance(pqp):
         assert stc["converged"][0] == 0 and stc["iters"][0] == 40
         Yd, _, _ = s.solve(Fd=Fd, iters=40)
         assert np.array_equal(Yc, Yd)
+
+
+def test_sym_other_grids_and_sizes(pqp):
+    """The smallest size that leaves the on-chip kernel (N = 2369: 19 blocks, the last one 65 rows wide), a size whose last
+    float4 of y is partial, and a grid of 64 CTAs (PQP_GEMV_GRID): the upper-triangle loop against the full-matrix loop, plus
+    the same bits from run to run.  Nothing here depends on the SM count except the cut of the unit ranges."""
+    import os
+    rng = np.random.default_rng(33)
+    for N, grid in ((2369, None), (2817, None), (2560, 64), (3330, 100)):
+        Qd = spd_dual(rng, N, N + 300)
+        Fd = rng.uniform(-50, 50, N).astype(np.float32)
+        if grid:
+            os.environ["PQP_GEMV_GRID"] = str(grid)
+        try:
+            with pqp.Solver(Qd=Qd) as s:
+                Y, _, st = s.solve(Fd=Fd, iters=25)
+                assert s.last_kernel.startswith("gemv_sym"), (N, grid, s.last_kernel)
+                Y2, _, _ = s.solve(Fd=Fd, iters=25)
+                assert np.array_equal(Y, Y2)
+            with pqp.Solver(Qd=Qd, exploit_symmetry=0) as s:
+                Yf, _, stf = s.solve(Fd=Fd, iters=25)
+        finally:
+            os.environ.pop("PQP_GEMV_GRID", None)
+        assert relerr(Y[0], Yf[0]) <= TOL, (N, grid, relerr(Y[0], Yf[0]))
+        np.testing.assert_allclose(st["Jd"][0], stf["Jd"][0], rtol=1e-4)
