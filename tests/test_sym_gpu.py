@@ -174,3 +174,20 @@ def test_sym_other_grids_and_sizes(pqp):
             os.environ.pop("PQP_GEMV_GRID", None)
         assert relerr(Y[0], Yf[0]) <= TOL, (N, grid, relerr(Y[0], Yf[0]))
         np.testing.assert_allclose(st["Jd"][0], stf["Jd"][0], rtol=1e-4)
+
+
+def test_sym_several_right_hand_sides_in_one_call(pqp):
+    """pqp_solve_dual with B = 3 on a dual too large for the batched tensor-core kernel: three runs of the upper-triangle
+    loop on the same unit array, each equal to its own single solve (the per-row constants are rebuilt per launch)."""
+    rng = np.random.default_rng(44)
+    N = 2560
+    Qd = spd_dual(rng, N, 2900)
+    Fd = rng.uniform(-50, 50, (3, N)).astype(np.float32)
+    with pqp.Solver(Qd=Qd, batch_capacity=3) as s:
+        Y, _, st = s.solve(Fd=Fd, iters=20)
+        assert s.last_kernel.startswith("gemv_sym"), s.last_kernel
+        assert Y.shape == (3, N) and np.all(st["iters"] == 20)
+        for b in range(3):
+            Yb, _, stb = s.solve(Fd=Fd[b], iters=20)
+            assert np.array_equal(Y[b], Yb[0]), b
+            np.testing.assert_allclose(st["Jd"][b], stb["Jd"][0], rtol=1e-6)
