@@ -52,7 +52,7 @@
 #define SY_RC 6                     /* per owned row: theta+q-, theta+q+, Fd, slack tolerance, y, previous y */
 #define SY_D 4                      /* units in flight per warp (cp.async groups) */
 #define SY_TPR 4                    /* threads per owned row in the owner phase (64 rows per round) */
-#define SY_OB 19                    /* packets in flight per owner thread */
+#define SY_OB 18                    /* packets in flight per owner thread */
 #define SY_YB 4                     /* float4 of y in flight per thread */
 
 #ifdef PQP_SYM_DEBUG
@@ -380,8 +380,8 @@ template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_ke
 		if (p == 0) {
 			for (int i = tid; i < N; i += SY_CONS) y_s[i] = __ldcg(a.ybuf0 + i);
 		} else {
-			/* one burst of polling loads; while packets are missing a thread spins on ONE float4 only (many loads in flight per thread
-			 * while the packets are not there yet saturate the L2 with polls: measured +9 us per update at N=8192) */
+			/* every thread spins on ONE float4 (many loads in flight per thread while the packets are not there yet saturate the
+			 * L2 with polls: measured +9 us per update at N=8192), then takes the rest of its share in one batch */
 			for (int xb = tid; xb < nneed4; xb += SY_YB * SY_CONS) {
 				uint4 lo[SY_YB], hi[SY_YB];
 				int cc[SY_YB];
@@ -390,42 +390,34 @@ template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_ke
 					const int x = xb + q * SY_CONS;
 					cc[q] = x < nneed4 ? need[1 + x / (SY_BS / 4)] * (SY_BS / 4) + x % (SY_BS / 4) : n4;
 				}
+				if (cc[0] < n4) {
+					lo[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0]));
+					hi[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0] + 2));
+					while (lo[0].y != (uint32_t)p || lo[0].w != (uint32_t)p || hi[0].y != (uint32_t)p || hi[0].w != (uint32_t)p) {
+						__nanosleep(20);
+						lo[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0]));
+						hi[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0] + 2));
+					}
+				}
 #pragma unroll
-				for (int q = 0; q < SY_YB; q++) {
+				for (int q = 1; q < SY_YB; q++) {
 					if (cc[q] < n4) {
 						lo[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[q]));
 						hi[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[q] + 2));
 					}
 				}
-				bool again;
-				do {
-					again = false;
-					bool spun = false;
-#pragma unroll
-					for (int q = 0; q < SY_YB; q++) {
-						const int c = cc[q];
-						if (c < n4 && (lo[q].y != (uint32_t)p || lo[q].w != (uint32_t)p || hi[q].y != (uint32_t)p || hi[q].w != (uint32_t)p)) {
-							if (!spun) {
-								do {
-									__nanosleep(20);
-									lo[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c));
-									hi[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c + 2));
-								} while (lo[q].y != (uint32_t)p || lo[q].w != (uint32_t)p || hi[q].y != (uint32_t)p || hi[q].w != (uint32_t)p);
-								spun = true;
-							} else {
-								lo[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c));
-								hi[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c + 2));
-								if (lo[q].y != (uint32_t)p || lo[q].w != (uint32_t)p || hi[q].y != (uint32_t)p || hi[q].w != (uint32_t)p) again = true;
-							}
-						}
-					}
-				} while (again);
 #pragma unroll
 				for (int q = 0; q < SY_YB; q++) {
 					const int c = cc[q];
-					if (c < n4)
+					if (c < n4) {
+						while (lo[q].y != (uint32_t)p || lo[q].w != (uint32_t)p || hi[q].y != (uint32_t)p || hi[q].w != (uint32_t)p) {
+							__nanosleep(20);
+							lo[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c));
+							hi[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c + 2));
+						}
 						reinterpret_cast<float4 *>(y_s)[c] = make_float4(__uint_as_float(lo[q].x), __uint_as_float(lo[q].z),
 												 __uint_as_float(hi[q].x), __uint_as_float(hi[q].z));
+					}
 				}
 			}
 			if (need[need[0]] == nb - 1) /* the last, partial float4 of y */
@@ -606,10 +598,18 @@ template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_ke
 					const int cc = c0 + (m - nr);
 					return cp_in + ((size_t)cc * g.maxseg + (Ib - tab_j0[cc])) * SY_BS + li;
 				};
-				/* terms k, k+SY_TPR, ... in ascending order.  One burst of up to SY_OB polling loads; if packets are missing the thread
-				 * spins on the FIRST missing one only (many loads in flight per thread while waiting saturate the L2 with polls), then
-				 * refreshes the others in one burst: one L2 round trip when everything is there, two otherwise. */
-				for (int m0 = k; m0 < nt; m0 += SY_TPR * SY_OB) {
+				/* terms k, k+SY_TPR, ... in ascending order: spin on the first, then SY_OB polling loads in flight */
+				if (k < nt) {
+					const uint4 *s0 = term(k);
+					uint4 v0 = ld_pair_raw(s0);
+					while (v0.y != ep || v0.w != ep) {
+						__nanosleep(20);
+						v0 = ld_pair_raw(s0);
+					}
+					num = __uint_as_float(v0.x);
+					den = __uint_as_float(v0.z);
+				}
+				for (int m0 = k + SY_TPR; m0 < nt; m0 += SY_TPR * SY_OB) {
 					const uint4 *src[SY_OB];
 					uint4 v[SY_OB];
 #pragma unroll
@@ -620,28 +620,13 @@ template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_ke
 #pragma unroll
 					for (int q = 0; q < SY_OB; q++)
 						if (src[q]) v[q] = ld_pair_raw(src[q]);
-					bool again;
-					do {
-						again = false;
-						bool spun = false;
-#pragma unroll
-						for (int q = 0; q < SY_OB; q++)
-							if (src[q] && (v[q].y != ep || v[q].w != ep)) {
-								if (!spun) {
-									do {
-										__nanosleep(20);
-										v[q] = ld_pair_raw(src[q]);
-									} while (v[q].y != ep || v[q].w != ep);
-									spun = true;
-								} else {
-									v[q] = ld_pair_raw(src[q]);
-									if (v[q].y != ep || v[q].w != ep) again = true;
-								}
-							}
-					} while (again);
 #pragma unroll
 					for (int q = 0; q < SY_OB; q++)
 						if (src[q]) {
+							while (v[q].y != ep || v[q].w != ep) {
+								__nanosleep(20);
+								v[q] = ld_pair_raw(src[q]);
+							}
 							num += __uint_as_float(v[q].x);
 							den += __uint_as_float(v[q].z);
 						}
