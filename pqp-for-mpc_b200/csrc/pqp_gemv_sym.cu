@@ -191,6 +191,105 @@ __device__ __forceinline__ void row_finish(float n0, float n1, float d0, float d
 	if ((lane & 3) == 0) st_pair(dst, num, den, ep);
 }
 
+/* y packets of pass p -> plain floats in shared memory, for the blocks listed in need[].  Not inlined: the polling buffers must
+ * not take part in the register allocation of the unit loop. */
+__device__ __noinline__ void sym_fetch_y(float *y_s, const uint2 *pk_in, const int *need, int nneed4, int n4, int N, int nb, uint32_t p, int tid)
+{
+	/* every thread spins on ONE float4 (many loads in flight per thread while the packets are not there yet saturate the
+	 * L2 with polls: measured +9 us per update at N=8192), then takes the rest of its share in one batch */
+	for (int xb = tid; xb < nneed4; xb += SY_YB * SY_CONS) {
+		uint4 lo[SY_YB], hi[SY_YB];
+		int cc[SY_YB];
+#pragma unroll
+		for (int q = 0; q < SY_YB; q++) {
+			const int x = xb + q * SY_CONS;
+			cc[q] = x < nneed4 ? need[1 + x / (SY_BS / 4)] * (SY_BS / 4) + x % (SY_BS / 4) : n4;
+		}
+		if (cc[0] < n4) {
+			lo[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0]));
+			hi[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0] + 2));
+			while (lo[0].y != p || lo[0].w != p || hi[0].y != p || hi[0].w != p) {
+				__nanosleep(20);
+				lo[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0]));
+				hi[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0] + 2));
+			}
+		}
+#pragma unroll
+		for (int q = 1; q < SY_YB; q++) {
+			if (cc[q] < n4) {
+				lo[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[q]));
+				hi[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[q] + 2));
+			}
+		}
+#pragma unroll
+		for (int q = 0; q < SY_YB; q++) {
+			const int c = cc[q];
+			if (c < n4) {
+				while (lo[q].y != p || lo[q].w != p || hi[q].y != p || hi[q].w != p) {
+					__nanosleep(20);
+					lo[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c));
+					hi[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c + 2));
+				}
+				reinterpret_cast<float4 *>(y_s)[c] = make_float4(__uint_as_float(lo[q].x), __uint_as_float(lo[q].z),
+										 __uint_as_float(hi[q].x), __uint_as_float(hi[q].z));
+			}
+		}
+	}
+	if (need[need[0]] == nb - 1) /* the last, partial float4 of y */
+		for (int i = 4 * n4 + tid; i < N; i += SY_CONS) y_s[i] = ld_packet(pk_in + i, p);
+}
+
+/* the packets of row i: thread group k of SY_TPR sums terms k, k+SY_TPR, ... in ascending order.  Not inlined (see above). */
+__device__ __noinline__ float2 sym_row_terms(const uint4 *rp_in, const uint4 *cp_in, const int *tab_c0, const int *tab_c1, const int *tab_j0,
+					      int nb, int maxseg, int i, int k, uint32_t ep)
+{
+	float num = 0.0f, den = 0.0f;
+	const int Ib = i / SY_BS, li = i % SY_BS;
+	const int nr = nb - Ib, c0 = tab_c0[Ib], nt = nr + tab_c1[Ib] - c0 + 1;
+	auto term = [&](int m) -> const uint4 * {
+		if (m < nr) {
+			const int J = Ib + m;
+			return rp_in + ((size_t)J * (J + 1) / 2 + Ib) * SY_BS + li;
+		}
+		const int cc = c0 + (m - nr);
+		return cp_in + ((size_t)cc * maxseg + (Ib - tab_j0[cc])) * SY_BS + li;
+	};
+	/* terms k, k+SY_TPR, ... in ascending order: spin on the first, then SY_OB polling loads in flight */
+	if (k < nt) {
+		const uint4 *s0 = term(k);
+		uint4 v0 = ld_pair_raw(s0);
+		while (v0.y != ep || v0.w != ep) {
+			__nanosleep(20);
+			v0 = ld_pair_raw(s0);
+		}
+		num = __uint_as_float(v0.x);
+		den = __uint_as_float(v0.z);
+	}
+	for (int m0 = k + SY_TPR; m0 < nt; m0 += SY_TPR * SY_OB) {
+		const uint4 *src[SY_OB];
+		uint4 v[SY_OB];
+#pragma unroll
+		for (int q = 0; q < SY_OB; q++) {
+			const int m = m0 + SY_TPR * q;
+			src[q] = m < nt ? term(m) : nullptr;
+		}
+#pragma unroll
+		for (int q = 0; q < SY_OB; q++)
+			if (src[q]) v[q] = ld_pair_raw(src[q]);
+#pragma unroll
+		for (int q = 0; q < SY_OB; q++)
+			if (src[q]) {
+				while (v[q].y != ep || v[q].w != ep) {
+					__nanosleep(20);
+					v[q] = ld_pair_raw(src[q]);
+				}
+				num += __uint_as_float(v[q].x);
+				den += __uint_as_float(v[q].z);
+			}
+	}
+	return make_float2(num, den);
+}
+
 } // namespace
 
 struct SymGeom {
@@ -380,48 +479,7 @@ template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_ke
 		if (p == 0) {
 			for (int i = tid; i < N; i += SY_CONS) y_s[i] = __ldcg(a.ybuf0 + i);
 		} else {
-			/* every thread spins on ONE float4 (many loads in flight per thread while the packets are not there yet saturate the
-			 * L2 with polls: measured +9 us per update at N=8192), then takes the rest of its share in one batch */
-			for (int xb = tid; xb < nneed4; xb += SY_YB * SY_CONS) {
-				uint4 lo[SY_YB], hi[SY_YB];
-				int cc[SY_YB];
-#pragma unroll
-				for (int q = 0; q < SY_YB; q++) {
-					const int x = xb + q * SY_CONS;
-					cc[q] = x < nneed4 ? need[1 + x / (SY_BS / 4)] * (SY_BS / 4) + x % (SY_BS / 4) : n4;
-				}
-				if (cc[0] < n4) {
-					lo[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0]));
-					hi[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0] + 2));
-					while (lo[0].y != (uint32_t)p || lo[0].w != (uint32_t)p || hi[0].y != (uint32_t)p || hi[0].w != (uint32_t)p) {
-						__nanosleep(20);
-						lo[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0]));
-						hi[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0] + 2));
-					}
-				}
-#pragma unroll
-				for (int q = 1; q < SY_YB; q++) {
-					if (cc[q] < n4) {
-						lo[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[q]));
-						hi[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[q] + 2));
-					}
-				}
-#pragma unroll
-				for (int q = 0; q < SY_YB; q++) {
-					const int c = cc[q];
-					if (c < n4) {
-						while (lo[q].y != (uint32_t)p || lo[q].w != (uint32_t)p || hi[q].y != (uint32_t)p || hi[q].w != (uint32_t)p) {
-							__nanosleep(20);
-							lo[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c));
-							hi[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c + 2));
-						}
-						reinterpret_cast<float4 *>(y_s)[c] = make_float4(__uint_as_float(lo[q].x), __uint_as_float(lo[q].z),
-												 __uint_as_float(hi[q].x), __uint_as_float(hi[q].z));
-					}
-				}
-			}
-			if (need[need[0]] == nb - 1) /* the last, partial float4 of y */
-				for (int i = 4 * n4 + tid; i < N; i += SY_CONS) y_s[i] = ld_packet(pk_in + i, (uint32_t)p);
+			sym_fetch_y(y_s, pk_in, need, nneed4, n4, N, nb, (uint32_t)p, tid);
 		}
 		consumer_sync();
 		if (TOL && pending) {
@@ -588,49 +646,9 @@ template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_ke
 			const bool valid = rr < nrows;
 			float num = 0.0f, den = 0.0f;
 			if (valid) {
-				const int i = r0 + rr, Ib = i / SY_BS, li = i % SY_BS;
-				const int nr = nb - Ib, c0 = tab_c0[Ib], nt = nr + tab_c1[Ib] - c0 + 1;
-				auto term = [&](int m) -> const uint4 * {
-					if (m < nr) {
-						const int J = Ib + m;
-						return rp_in + ((size_t)J * (J + 1) / 2 + Ib) * SY_BS + li;
-					}
-					const int cc = c0 + (m - nr);
-					return cp_in + ((size_t)cc * g.maxseg + (Ib - tab_j0[cc])) * SY_BS + li;
-				};
-				/* terms k, k+SY_TPR, ... in ascending order: spin on the first, then SY_OB polling loads in flight */
-				if (k < nt) {
-					const uint4 *s0 = term(k);
-					uint4 v0 = ld_pair_raw(s0);
-					while (v0.y != ep || v0.w != ep) {
-						__nanosleep(20);
-						v0 = ld_pair_raw(s0);
-					}
-					num = __uint_as_float(v0.x);
-					den = __uint_as_float(v0.z);
-				}
-				for (int m0 = k + SY_TPR; m0 < nt; m0 += SY_TPR * SY_OB) {
-					const uint4 *src[SY_OB];
-					uint4 v[SY_OB];
-#pragma unroll
-					for (int q = 0; q < SY_OB; q++) {
-						const int m = m0 + SY_TPR * q;
-						src[q] = m < nt ? term(m) : nullptr;
-					}
-#pragma unroll
-					for (int q = 0; q < SY_OB; q++)
-						if (src[q]) v[q] = ld_pair_raw(src[q]);
-#pragma unroll
-					for (int q = 0; q < SY_OB; q++)
-						if (src[q]) {
-							while (v[q].y != ep || v[q].w != ep) {
-								__nanosleep(20);
-								v[q] = ld_pair_raw(src[q]);
-							}
-							num += __uint_as_float(v[q].x);
-							den += __uint_as_float(v[q].z);
-						}
-				}
+				const float2 nd = sym_row_terms(rp_in, cp_in, tab_c0, tab_c1, tab_j0, nb, g.maxseg, r0 + rr, k, ep);
+				num = nd.x;
+				den = nd.y;
 			}
 			osum[k * (SY_CONS / SY_TPR) + tid % (SY_CONS / SY_TPR)] = make_float2(num, den);
 			consumer_sync();
