@@ -230,6 +230,14 @@ int pqp_shift_duals(pqp_handle *h, const float *Y, int B, float y_floor, float *
  */
 enum { PQP_MM_STRICT = 0, PQP_MM_SIMT = 1, PQP_MM_TENSOR = 2 };
 int pqp_matmul(float *out, const float *A, int tA, const float *B, int tB, int a, int b, int c, int engine, int device);
+/*
+ * One multiplicative update from the reference's own DENSE operands, for single-step tests against updateY2 + updY
+ * (PQP_CPU.c:603-618, :590-596): Y_next_i = (Qdn_theta[i,:]*Y + Fdn_i) / (Qdp_theta[i,:]*Y + Fdp_i) * Y_i, every sum k ascending
+ * with separately rounded multiply and add, IEEE division -- bit-identical to the reference.  Host or device pointers;
+ * matrices [N x N] row-major.  (The solver proper never forms these two matrices: it keeps one signed Qd and theta.)
+ */
+int pqp_update_y2(float *Y_next, const float *Y, const float *Qdp_theta, const float *Qdn_theta, const float *Fdp, const float *Fdn, int N,
+		  int device);
 
 /* ---- introspection (tests, benches) ----------------------------------------------------- */
 /* copies out what setup built; any pointer may be NULL.  Qd [N x N], theta [N], GQ [N x M] (host buffers) */

@@ -69,7 +69,7 @@ ABI_SYMBOLS = (
     "pqp_load_example", "pqp_load_testfile", "pqp_generate_testproblem", "pqp_write_testfile", "pqp_free_problem",
     "pqp_setup", "pqp_setup_dual", "pqp_destroy", "pqp_solve_batch", "pqp_solve_dual", "pqp_recover_primal",
     "pqp_solve_batch_primal", "pqp_get_dual", "pqp_get_linear_terms", "pqp_get_stream", "pqp_last_solve_ms",
-    "pqp_launch_count", "pqp_last_kernel", "pqp_device_qd", "pqp_matmul", "pqp_shift_duals", "pqp_output_offsets",
+    "pqp_launch_count", "pqp_last_kernel", "pqp_device_qd", "pqp_matmul", "pqp_shift_duals", "pqp_output_offsets", "pqp_update_y2",
 )
 MM_STRICT, MM_SIMT, MM_TENSOR = 0, 1, 2
 
@@ -221,6 +221,17 @@ def _numpy_to_problem(prob: dict):
             setattr(hp, name, a.ctypes.data_as(_FP))
     hp.Mp0 = float(prob.get("Mp0", 0.0))
     return hp, keep
+
+
+def update_y2(Y, Qdp_theta, Qdn_theta, Fdp, Fdn, device=-1):
+    """pqp_update_y2: one reference-order update from the dense split operands (updateY2 + updY, PQP_CPU.c:603-618, 590-596)."""
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    Y, Qp, Qn, Fdp, Fdn = f(Y), f(Qdp_theta), f(Qdn_theta), f(Fdp), f(Fdn)
+    out = np.empty_like(Y)
+    rc = lib().pqp_update_y2(_as_ptr(out), _as_ptr(Y), _as_ptr(Qp), _as_ptr(Qn), _as_ptr(Fdp), _as_ptr(Fdn), int(Y.size), int(device))
+    if rc:
+        raise PQPError(rc, "pqp_update_y2")
+    return out
 
 
 def output_offsets(d: Dims, Z, Theta):

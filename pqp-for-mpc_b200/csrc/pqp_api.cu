@@ -953,6 +953,38 @@ int pqp_shift_duals(pqp_handle *h, const float *Y, int B, float y_floor, float *
 	return PQP_OK;
 }
 
+/* ---- updateY2 + updY (PQP_CPU.c:603-618, 590-596) on the reference's dense operands ---- */
+int pqp_update_y2(float *Y_next, const float *Y, const float *Qdp_theta, const float *Qdn_theta, const float *Fdp, const float *Fdn, int N,
+		  int device)
+{
+	if (!Y_next || !Y || !Qdp_theta || !Qdn_theta || !Fdp || !Fdn || N <= 0) return PQP_ERR_INVALID;
+	if (pqp_device_count() == 0) return PQP_ERR_NO_DEVICE;
+	if (device >= 0) CK(cudaSetDevice(device));
+	float *dQp = NULL, *dQn = NULL, *dv = NULL; /* dv: Y | Fdp | Fdn | Yn */
+	int rc = PQP_OK;
+	if ((rc = dalloc(&dQp, (size_t)N * N)) || (rc = dalloc(&dQn, (size_t)N * N)) || (rc = dalloc(&dv, (size_t)4 * N))) goto done;
+	{
+		const size_t nn = (size_t)N * N * sizeof(float), nv = (size_t)N * sizeof(float);
+		cudaError_t e = cudaMemcpy(dQp, Qdp_theta, nn, cudaMemcpyDefault);
+		if (e == cudaSuccess) e = cudaMemcpy(dQn, Qdn_theta, nn, cudaMemcpyDefault);
+		if (e == cudaSuccess) e = cudaMemcpy(dv, Y, nv, cudaMemcpyDefault);
+		if (e == cudaSuccess) e = cudaMemcpy(dv + N, Fdp, nv, cudaMemcpyDefault);
+		if (e == cudaSuccess) e = cudaMemcpy(dv + 2 * (size_t)N, Fdn, nv, cudaMemcpyDefault);
+		if (e == cudaSuccess) e = pqp_launch_update_y2_dense(dv + 3 * (size_t)N, dv, dQp, dQn, dv + N, dv + 2 * (size_t)N, N, 0);
+		if (e == cudaSuccess) e = cudaMemcpy(Y_next, dv + 3 * (size_t)N, nv, cudaMemcpyDefault);
+		if (e != cudaSuccess) {
+			snprintf(g_cuda_err, sizeof g_cuda_err, "pqp_update_y2 -> %s", cudaGetErrorString(e));
+			cudaGetLastError();
+			rc = PQP_ERR_CUDA;
+		}
+	}
+done:
+	if (dQp) cudaFree(dQp);
+	if (dQn) cudaFree(dQn);
+	if (dv) cudaFree(dv);
+	return rc;
+}
+
 /* ---- matrixMultiply (PQP_CPU.c:84-147) on the device ---------------------------------------- */
 int pqp_matmul(float *out, const float *A, int tA, const float *B, int tB, int a, int b, int c, int engine, int device)
 {

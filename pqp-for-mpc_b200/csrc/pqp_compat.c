@@ -158,7 +158,13 @@ float computeCost(float *Z, float *Q, float *F, float *M, int N)
 }
 
 /*
- * Not provided: updateY2 (PQP_CPU.c:603).  Its arguments are the two dense split matrices
- * Qdp_theta / Qdn_theta, which this solver never materialises (one signed Qd + a theta vector);
- * a single reference update is pqp_solve_dual(h, Fd, 1, 1, Y, Y_next, NULL).
+ * PQP_CPU.c:603 (+ updY, :590-596, which the reference calls from inside it): one update from the two dense split matrices.
+ * The solver proper never forms them (one signed Qd + a theta vector); this shim exists for single-step tests and is
+ * bit-identical to the reference whatever pqp_compat_set_order says.  Fd is unused by the reference's body as well.
  */
+void updateY2(float *Y_next, float *Y, float *Qdp_theta, float *Qdn_theta, float *Fd, float *Fdp, float *Fdn, int N)
+{
+	(void)Fd;
+	int rc = pqp_update_y2(Y_next, Y, Qdp_theta, Qdn_theta, Fdp, Fdn, N, -1);
+	if (rc) complain("updateY2/pqp_update_y2", rc);
+}

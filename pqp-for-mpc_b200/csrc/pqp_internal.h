@@ -53,6 +53,9 @@ cudaError_t pqp_launch_recover(float *U, float *tmp, const float *Y, int ldy, co
 			       const float *Qp_inv, int B, int N, int M, int strict, cudaStream_t s);
 /* receding-horizon shift of the duals (out must not alias in) */
 cudaError_t pqp_launch_shift_duals(float *out, const float *in, int B, int pH, int nI, float y_floor, cudaStream_t s);
+/* Yn = Y .* (Qn*Y + Fdn) ./ (Qp*Y + Fdp), reference order (updateY2 + updY); all device pointers */
+cudaError_t pqp_launch_update_y2_dense(float *Yn, const float *Y, const float *Qp, const float *Qn, const float *Fdp, const float *Fdn, int N,
+				       cudaStream_t s);
 /* fill n floats */
 cudaError_t pqp_launch_fill(float *p, float v, size_t n, cudaStream_t s);
 

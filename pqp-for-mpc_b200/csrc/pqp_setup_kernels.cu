@@ -516,3 +516,24 @@ cudaError_t pqp_launch_fd_offsets(float *Fd, const float *Kx, const float *X, in
 	}
 	return cudaGetLastError();
 }
+
+/* ---- updateY2 + updY on the reference's dense split operands (single-step parity instrument, PQP_CPU.c:603-618, 590-596) ---- */
+__global__ void update_y2_dense_kernel(float *Yn, const float *Y, const float *Qp, const float *Qn, const float *Fdp, const float *Fdn, int N)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= N) return;
+	const float *rn = Qn + (size_t)i * N, *rp = Qp + (size_t)i * N;
+	float num = 0.0f, den = 0.0f;
+	for (int k = 0; k < N; k++) num = __fadd_rn(num, __fmul_rn(rn[k], Y[k]));
+	for (int k = 0; k < N; k++) den = __fadd_rn(den, __fmul_rn(rp[k], Y[k]));
+	num = __fadd_rn(num, Fdn[i]);
+	den = __fadd_rn(den, Fdp[i]);
+	Yn[i] = __fmul_rn(__fdiv_rn(num, den), Y[i]);
+}
+
+cudaError_t pqp_launch_update_y2_dense(float *Yn, const float *Y, const float *Qp, const float *Qn, const float *Fdp, const float *Fdn, int N,
+				       cudaStream_t s)
+{
+	update_y2_dense_kernel<<<(N + 63) / 64, 64, 0, s>>>(Yn, Y, Qp, Qn, Fdp, Fdn, N);
+	return cudaGetLastError();
+}

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(pqp):
     for name in declared:
         assert hasattr(L, name), name
     compat = C.CDLL(pqp.COMPAT_PATH)
-    for name in ("convertToDual", "solveQuadraticDual", "computeUfromY", "computeFp", "computeCost",
+    for name in ("convertToDual", "solveQuadraticDual", "computeUfromY", "computeFp", "computeCost", "updateY2",
                  "pqp_compat_set_dims", "pqp_compat_set_order", "pqp_compat_set_fixed_iters"):
         assert hasattr(compat, name), name
 

@@ -410,3 +410,39 @@ def test_state_dependent_constraint_offsets(pqp, oracle32, oracle64):
         s.solve(X, iters=1)
         Fd2, _ = s.linear_terms(B)
         assert np.array_equal(Fd2, Fd0)
+
+
+def test_single_update_from_the_dense_split_operands(pqp, oracle32):
+    """updateY2 + updY (PQP_CPU.c:603-618, 590-596) on the reference's own dense Qdp_theta / Qdn_theta: pqp_update_y2 and the
+    compat library's updateY2 shim are bit-identical to the oracle's step, for the example and a generator instance."""
+    compat = C.CDLL(pqp.COMPAT_PATH)
+    fp = C.POINTER(C.c_float)
+    compat.updateY2.argtypes = [fp] * 7 + [C.c_int]
+    compat.updateY2.restype = None
+    rng = np.random.default_rng(8)
+    cases = []
+    g = np.load(os.path.join(GOLDEN, "golden_example.npz"))
+    cases.append((g["Qd"], g["Fd"]))
+    prob, d = pqp.generate_testproblem(5, 96, 200)
+    with pqp.Solver(d, prob, order=pqp.ORDER_STRICT) as s:
+        s.solve(iters=1)
+        Qd, _, _ = s.dual(want_gq=False)
+        Fd, _ = s.linear_terms(1)
+    cases.append((Qd, Fd[0]))
+    for Qd, Fd in cases:
+        N = Fd.size
+        th = oracle32.theta(Qd)
+        Qp, Qn = oracle32.split(Qd, th)
+        Fdp, Fdn = np.maximum(Fd, 0).astype(np.float32), np.maximum(-Fd, 0).astype(np.float32)
+        Y = rng.uniform(0.5, 1500.0, N).astype(np.float32)
+        want = oracle32.update_y2(Y, Qp, Qn, Fd)
+        got = pqp.update_y2(Y, Qp, Qn, Fdp, Fdn)
+        assert np.array_equal(got, want)
+        out = np.zeros(N, np.float32)
+        a = [np.ascontiguousarray(x, np.float32) for x in (out, Y, Qp, Qn, Fd, Fdp, Fdn)]
+        compat.updateY2(*[x.ctypes.data_as(fp) for x in a], N)
+        assert np.array_equal(a[0], want)
+        # and the solver's own STRICT step (signed Qd + theta, never the dense pair) gives the same bits
+        with pqp.Solver(Qd=Qd, order=pqp.ORDER_STRICT) as s:
+            Y1, _, _ = s.solve(Fd=Fd, iters=1, Y0=Y)
+            assert np.array_equal(Y1[0], want)
