@@ -159,13 +159,17 @@ class Oracle(_Base):
         return Y
 
     def solve_converge(self, Qd, Fd, Md, Qp, Qp_inv, Fp, Mp, Gp, Kp, y_init=1000.0, theta_floor=5.0,
-                       max_h=10 ** 7):
+                       max_h=10 ** 7, tol=None):
+        """tol=None: the reference's 1e-6 (PQP_CPU.c:19-22); a number: the same test with erc = eac = eaj = erj = tol."""
         Qd, Fd, Qp, Qp_inv, Fp, Gp, Kp = map(self.arr, (Qd, Fd, Qp, Qp_inv, Fp, Gp, Kp))
         N, M = Gp.shape
         Y, U, md, mp = self.zeros(N), self.zeros(M), self.arr([Md]), self.arr([Mp])
-        h = self._f("solve_converge", C.c_long)(
-            _ptr(Y), _ptr(U), _ptr(Qd), _ptr(Fd), _ptr(md), _ptr(Qp), _ptr(Qp_inv), _ptr(Fp), _ptr(mp),
-            _ptr(Gp), _ptr(Kp), C.c_int(N), C.c_int(M), self.real(y_init), self.real(theta_floor), C.c_long(max_h))
+        args = (_ptr(Y), _ptr(U), _ptr(Qd), _ptr(Fd), _ptr(md), _ptr(Qp), _ptr(Qp_inv), _ptr(Fp), _ptr(mp),
+                _ptr(Gp), _ptr(Kp), C.c_int(N), C.c_int(M), self.real(y_init), self.real(theta_floor), C.c_long(max_h))
+        if tol is None:
+            h = self._f("solve_converge", C.c_long)(*args)
+        else:
+            h = self._f("solve_converge_tol", C.c_long)(*args, C.c_double(tol))
         return Y, U, int(h)
 
 

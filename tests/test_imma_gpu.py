@@ -201,3 +201,32 @@ def test_receding_horizon_warm_start(pqp, oracle32):
     its_w = sum(int(st["iters"][ok].sum()) for st in stw[1:])
     assert its_w < 0.8 * its_c, (its_w, its_c)
     assert np.abs(Xw[-1][ok]).mean() < np.abs(Xw[0][ok]).mean()        # the loop regulates
+
+
+def test_stopping_points_against_the_reference_stop_test(pqp, oracle32):
+    """SURVEY 8(f)3, statistically: terminate() (PQP_CPU.c:673-687, oracle restatement, float32, the reference's 1e-6) against the
+    fused stop test of the CUDA loop on g = Qd y + Fd, checked after every update, on 16 small condensed-MPC states.  The
+    reference's first condition carries no tolerance (it waits for Jp <= -Jd, which float32 reaches on rounding noise), so
+    the counts are compared as a distribution: every state stops, within a few percent of the reference's count in the
+    median and never far from it, at the same primal solution (tools/convergence_stats.py prints the table)."""
+    from bench_problems import condensed_mpc
+    n, cap, tol = 16, 30000, 1e-6
+    mp, md, X = condensed_mpc(11, pH=6, nS=4, nI=2, n_states=n, x_scale=25.0)
+    o = oracle32
+    Qp = o.gauss_jordan(mp["Qp_inv"])
+    ref = []
+    for b in range(n):
+        Fp = o.compute_fp(mp["Fp1"], mp["Fp2"], mp["Fp3"], mp["D"], X[b])
+        Mp = o.compute_mp(*[mp[k] for k in ("Mp1", "Mp2", "Mp3", "Mp4", "Mp5", "Mp6")], mp["D"], X[b])
+        Qd, Fd, Md, _ = o.convert_to_dual(mp["Qp_inv"], mp["Gp"], mp["Kp"], Fp, Mp)
+        Y, U, h = o.solve_converge(Qd, Fd, Md, Qp, mp["Qp_inv"], Fp, Mp, mp["Gp"], mp["Kp"], max_h=cap)
+        assert h < cap
+        ref.append((h - 1, U))
+    with pqp.Solver(md, mp, eaj=tol, erj=tol, erc=tol, eac=tol, check_every=1, max_iters=cap, batch_capacity=n) as s:
+        Y, U, st = s.solve(X, iters=0, primal=True)
+    assert np.all(st["converged"] == 1)
+    ratio = np.array([st["iters"][b] / max(ref[b][0], 1) for b in range(n)])
+    print("ours / reference update counts: median %.3f min %.3f max %.3f" % (np.median(ratio), ratio.min(), ratio.max()))
+    assert 0.9 <= np.median(ratio) <= 1.1 and ratio.min() >= 0.7 and ratio.max() <= 1.5
+    for b in range(n):
+        assert np.abs(U[b] - ref[b][1]).max() <= 2e-4 * max(np.abs(ref[b][1]).max(), 1.0), b
