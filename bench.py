@@ -9,6 +9,7 @@ Workloads (BASELINE.json configs):
                 target is stated on.  A *step* is one solve (I updates).  A single problem does not shard
                 ("replicas only"): with N GPUs every rank solves its own replica.
   c2            same distribution, N=1024, M=512, seed 12345 (Q on-chip resident; barrier-latency bound).
+  c1            the shipped example (N=28), 312 updates per solve = where PQP_CPU.c stops; latency only (config.us_per_solve).
   c4            batched MPC: 4096 states per GPU sharing one Hessian (horizon 30, 12 states, 4 inputs, N=480);
                 a step is one batch solve of I updates; problems shard over ranks with no collective in the loop
                 and one NCCL all-gather of U at the end of every step (inside the timed region).
@@ -42,6 +43,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
+    # the shipped example (a correctness config, latency only): 312 updates = where PQP_CPU.c itself stops
+    "c1": dict(kind="single", example=True, N=28, M=7, seed=0, iters=312),
     "c3": dict(kind="single", N=8192, M=2048, seed=12346),
     "c2": dict(kind="single", N=1024, M=512, seed=12345),
     "c4": dict(kind="batched", pH=30, nS=12, nI=4, B=4096, seed=2024),
@@ -163,6 +166,14 @@ def cpu_engine():
 def single_problem_host(w):
     """Host-side instance + its dual, formed with numpy BLAS (input preparation for the CPU arm, never timed)."""
     import pqp_for_mpc_b200 as pqp
+    if w.get("example"):
+        prob, d = pqp.load_example(os.path.join(ROOT, "tests", "golden", "example"))
+        nO = d.M
+        Fp = prob["Fp1"].reshape(d.M, -1) @ prob["D"] + prob["Fp2"].reshape(d.M, -1) @ prob["x"] - prob["Fp3"]
+        GQ = prob["Gp"].reshape(d.N, d.M) @ prob["Qp_inv"].reshape(d.M, d.M)
+        Qd = GQ @ prob["Gp"].reshape(d.N, d.M).T
+        Fd = GQ @ Fp + prob["Kp"]
+        return prob, d, np.ascontiguousarray(Qd, np.float32), np.ascontiguousarray(Fd, np.float32)
     prob, d = pqp.generate_testproblem(w["seed"], w["M"], w["N"])
     q = np.diag(prob["Qp_inv"]).astype(np.float32)
     GQ = prob["Gp"] * q[None, :]
@@ -309,11 +320,14 @@ def run_ours(args, w, rank, world, local_rank):
 
     if w["kind"] == "single":
         N, M = w["N"], w["M"]
-        prob, d = pqp.generate_testproblem(w["seed"], M, N)
+        if w.get("example"):
+            prob, d = pqp.load_example(os.path.join(ROOT, "tests", "golden", "example"))
+        else:
+            prob, d = pqp.generate_testproblem(w["seed"], M, N)
         s = pqp.Solver(d, prob, device=local_rank)
         ldq = (N + 31) // 32 * 32
         # device-resident leg: Fd and Y stay on the GPU
-        s.solve(iters=1, status=False)
+        s.solve(prob["x"][None] if w.get("example") else None, iters=1, status=False)
         Fd_host, _ = s.linear_terms(1)
         Fd_dev = torch.from_numpy(Fd_host[0]).cuda()
         Y_dev = torch.empty(N, dtype=torch.float32, device="cuda")
@@ -355,7 +369,9 @@ def run_ours(args, w, rank, world, local_rank):
 
         result.update(metric="pqp_iters_per_sec", unit="iterations/s", value=value, ms_per_step=ms / args.steps,
                       config={"workload": args.workload, "N": N, "M": M, "seed": w["seed"], "iters_per_step": args.iters,
-                              "generator": "testing/test_generator.c distribution, splitmix64-seeded", "kernel": kernel,
+                              "generator": ("example/*.txt as shipped" if w.get("example") else
+                                            "testing/test_generator.c distribution, splitmix64-seeded"), "kernel": kernel,
+                              "us_per_solve": 1e3 * ms / args.steps,
                               "parallelism": "replicas only (a single problem does not shard)" if world > 1 else "1 GPU",
                               "l2": ("one step = one launch of iters_per_step updates, Q re-read on every update; the loop reads the upper "
                                      "triangle of the symmetric Qd (134 MB at N=8192, about the size of L2): what stays in L2 / shared "
@@ -472,7 +488,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--iters", type=int, default=1000, help="PQP updates per solve (NUM_ITER, PQP_CPU.c:24)")
+    ap.add_argument("--iters", type=int, default=None, help="PQP updates per solve (default 1000 = NUM_ITER, PQP_CPU.c:24; c1: 312)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-batched", action="store_true", help="c3 only: skip the appended c4 leg")
     args = ap.parse_args()
@@ -482,6 +498,8 @@ def main():
         print(f"bench.py: --gpus {args.gpus} needs torchrun (python -m torch.distributed.run --nproc-per-node {args.gpus} ...); "
               "running 1 rank", file=sys.stderr)
     w = WORKLOADS[args.workload]
+    if args.iters is None:
+        args.iters = w.get("iters", 1000)
     if args.impl == "reference":
         run_reference(args, w, rank, world)
     else:
