@@ -637,6 +637,14 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		return PQP_OK;
 	}
 
+	if (pqp_gemv_cta_supported(N) && !(getenv("PQP_GEMV_CTA") && atoi(getenv("PQP_GEMV_CTA")) == 0)) {
+		/* a problem that fits one thread block: no exchange through L2 at all */
+		h->last_kernel = iters > 0 ? "gemv_cta" : "gemv_cta_tol";
+		CK(pqp_launch_gemv_cta(&a, h->stream));
+		h->launches++;
+		*y_res = h->ybuf1;
+		return PQP_OK;
+	}
 	if (h->gemv_grid <= 0) return PQP_ERR_UNSUPPORTED;
 	if (h->small_ok && !(iters <= 0 && getenv("PQP_GEMV_SMALL_TOL") && atoi(getenv("PQP_GEMV_SMALL_TOL")) == 0)) {
 		/* fixed count, or run to tolerance with the stop test evaluated in the kernel every check_every updates */

@@ -88,6 +88,9 @@ int pqp_gemv_tma_plan(int N, int ldq, int grid, size_t smem_budget, int *stages,
  * result is left in ybuf1 when packets are used, in ybuf[iters&1] otherwise */
 cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident, int pinned, int yc, void *pk0, void *pk1,
 				cudaStream_t s);
+/* one-CTA variant for N <= 128 (pqp_gemv_cta.cu): fixed count or run to tolerance; result left in ybuf1, status written */
+int pqp_gemv_cta_supported(int N);
+cudaError_t pqp_launch_gemv_cta(const pqp_gemv_args *a, cudaStream_t s);
 /* register-resident variant for small N (pqp_gemv_small.cu); result left in ybuf1 */
 int pqp_gemv_small_plan(int N, int ldq, int grid, int *wpr, int *cpt);
 cudaError_t pqp_launch_gemv_small(const pqp_gemv_args *a, int wpr, int cpt, void *pk0, void *pk1, cudaStream_t s);
