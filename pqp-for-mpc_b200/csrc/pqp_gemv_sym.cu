@@ -26,7 +26,7 @@
  *                column direction cn/cd[col] += max(-+q,0) * y_I[row]   -> stays in registers for the whole strip; at a
  *                                 strip change the sums are folded over a, added over the 8 warps in fixed order through
  *                                 shared memory and leave as one packet per (CTA, strip, column)
- *              arithmetic in packed pairs (fma.rn.f32x2): 80 FFMA2 + 32 FMNMX per lane and unit.
+ *              arithmetic in packed pairs (fma.rn.f32x2): 64 FFMA2 + 64 FMNMX per lane and unit.
  *   owners     CTA c also owns rows [N*c/G, N*(c+1)/G): lanes along consecutive rows (their packets are contiguous), four
  *              thread groups over the terms of a row (row direction: one per tile of its tile row; column direction: one per
  *              CTA that touched its strip), summed in fixed order; then (theta_i + max(-+q_ii,0)) y_i and F-+, the update
@@ -159,14 +159,15 @@ __device__ __forceinline__ u64 shfl2(u64 v, int o)
 	return pk2(__shfl_xor_sync(0xffffffffu, l, o), __shfl_xor_sync(0xffffffffu, h, o));
 }
 
-/* one float4 of one row: p = max(q,0), n = p - q = max(-q,0) (exact); row sums against y_J, column sums against y_I */
+/* one float4 of one row: p = max(q,0), n = max(-q,0); row sums against y_J, column sums against y_I */
 __device__ __forceinline__ void sym_row(const float4 q, const u64 yj01, const u64 yj23, const float yi, const u64 neg1, u64 &rn, u64 &rd,
 					u64 &cn01, u64 &cn23, u64 &cd01, u64 &cd23)
 {
 	const u64 yi2 = pk2(yi, yi);
-	const u64 q01 = pk2(q.x, q.y), q23 = pk2(q.z, q.w);
 	const u64 p01 = pk2(fmaxf(q.x, 0.0f), fmaxf(q.y, 0.0f)), p23 = pk2(fmaxf(q.z, 0.0f), fmaxf(q.w, 0.0f));
-	const u64 n01 = fma2(q01, neg1, p01), n23 = fma2(q23, neg1, p23);
+	/* max(-q,0) on the ALU pipe (p - q through the FMA pipe is the same value, measured 1% slower: the FMA pipe is the busier one) */
+	const u64 n01 = pk2(fmaxf(-q.x, 0.0f), fmaxf(-q.y, 0.0f)), n23 = pk2(fmaxf(-q.z, 0.0f), fmaxf(-q.w, 0.0f));
+	(void)neg1;
 	rd = fma2(p01, yj01, rd);
 	rn = fma2(n01, yj01, rn);
 	cd01 = fma2(p01, yi2, cd01);
