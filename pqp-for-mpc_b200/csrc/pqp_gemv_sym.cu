@@ -881,6 +881,14 @@ int pqp_gemv_sym_tables(int N, int G, int *cta_u0, int *cta_j0, int *strip_c0, i
 	return maxseg;
 }
 
+/* the host tables, for the CPU-side tests (not part of include/pqp.h); returns maxseg and the unit / block counts */
+extern "C" int pqp_internal_sym_tables(int N, int G, int *cta_u0, int *cta_j0, int *strip_c0, int *strip_c1, int *nb, int *U)
+{
+	pqp_gemv_sym_counts(N, nb, U);
+	if (*U < G) return 0;
+	return pqp_gemv_sym_tables(N, G, cta_u0, cta_j0, strip_c0, strip_c1);
+}
+
 static size_t sym_smem_bytes(int nb, int rows_max, int resident)
 {
 	return sizeof(float) * ((size_t)(SY_D + resident) * SY_UNIT + (size_t)nb * SY_BS + 4 * SY_WARPS * SY_BS + 2 * SY_CONS + SY_RC * (size_t)rows_max +
