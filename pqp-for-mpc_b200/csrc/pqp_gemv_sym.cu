@@ -77,6 +77,14 @@ __device__ __forceinline__ uint64_t make_policy(int kind)
 	}
 	return p;
 }
+/* back-off between two polls of a packet that is not there yet.  A wait in this kernel lasts microseconds; one that lasts seconds
+ * means a packet will never come (a defect): trap, so that the launch fails instead of hanging the device. */
+#define SY_SPIN_LIMIT (1u << 23)
+__device__ __forceinline__ void spin_pause(unsigned &spins)
+{
+	__nanosleep(20);
+	if (++spins > SY_SPIN_LIMIT) __trap();
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SY_CONS) : "memory"); }
 
 __device__ __forceinline__ void grid_barrier_consumers(unsigned *counter, unsigned &target, unsigned nblocks)
@@ -86,9 +94,10 @@ __device__ __forceinline__ void grid_barrier_consumers(unsigned *counter, unsign
 		target += nblocks;
 		__threadfence();
 		asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-		unsigned v;
+		unsigned v, spins = 0;
 		do {
 			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+			if (++spins > (SY_SPIN_LIMIT << 2)) __trap();
 		} while ((int)(v - target) < 0);
 		__threadfence();
 	}
@@ -103,10 +112,11 @@ __device__ __forceinline__ void st_packet(uint2 *dst, float v, uint32_t epoch)
 __device__ __forceinline__ float ld_packet(const uint2 *src, uint32_t epoch)
 {
 	uint32_t v, e;
+	unsigned spins = 0;
 	for (;;) {
 		asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(e) : "l"(src) : "memory");
 		if (e == epoch) break;
-		__nanosleep(20);
+		spin_pause(spins);
 	}
 	return __uint_as_float(v);
 }
@@ -196,6 +206,7 @@ __device__ __forceinline__ void row_finish(float n0, float n1, float d0, float d
  * not take part in the register allocation of the unit loop. */
 __device__ __noinline__ void sym_fetch_y(float *y_s, const uint2 *pk_in, const int *need, int nneed4, int n4, int N, int nb, uint32_t p, int tid)
 {
+	unsigned spins = 0;
 	/* every thread spins on ONE float4 (many loads in flight per thread while the packets are not there yet saturate the
 	 * L2 with polls: measured +9 us per update at N=8192), then takes the rest of its share in one batch */
 	for (int xb = tid; xb < nneed4; xb += SY_YB * SY_CONS) {
@@ -210,7 +221,7 @@ __device__ __noinline__ void sym_fetch_y(float *y_s, const uint2 *pk_in, const i
 			lo[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0]));
 			hi[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0] + 2));
 			while (lo[0].y != p || lo[0].w != p || hi[0].y != p || hi[0].w != p) {
-				__nanosleep(20);
+				spin_pause(spins);
 				lo[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0]));
 				hi[0] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * cc[0] + 2));
 			}
@@ -227,7 +238,7 @@ __device__ __noinline__ void sym_fetch_y(float *y_s, const uint2 *pk_in, const i
 			const int c = cc[q];
 			if (c < n4) {
 				while (lo[q].y != p || lo[q].w != p || hi[q].y != p || hi[q].w != p) {
-					__nanosleep(20);
+					spin_pause(spins);
 					lo[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c));
 					hi[q] = ld_pair_raw(reinterpret_cast<const uint4 *>(pk_in + 4 * c + 2));
 				}
@@ -245,6 +256,7 @@ __device__ __noinline__ float2 sym_row_terms(const uint4 *rp_in, const uint4 *cp
 					      int nb, int maxseg, int i, int k, uint32_t ep)
 {
 	float num = 0.0f, den = 0.0f;
+	unsigned spins = 0;
 	const int Ib = i / SY_BS, li = i % SY_BS;
 	const int nr = nb - Ib, c0 = tab_c0[Ib], nt = nr + tab_c1[Ib] - c0 + 1;
 	auto term = [&](int m) -> const uint4 * {
@@ -260,7 +272,7 @@ __device__ __noinline__ float2 sym_row_terms(const uint4 *rp_in, const uint4 *cp
 		const uint4 *s0 = term(k);
 		uint4 v0 = ld_pair_raw(s0);
 		while (v0.y != ep || v0.w != ep) {
-			__nanosleep(20);
+			spin_pause(spins);
 			v0 = ld_pair_raw(s0);
 		}
 		num = __uint_as_float(v0.x);
@@ -281,7 +293,7 @@ __device__ __noinline__ float2 sym_row_terms(const uint4 *rp_in, const uint4 *cp
 		for (int q = 0; q < SY_OB; q++)
 			if (src[q]) {
 				while (v[q].y != ep || v[q].w != ep) {
-					__nanosleep(20);
+					spin_pause(spins);
 					v[q] = ld_pair_raw(src[q]);
 				}
 				num += __uint_as_float(v[q].x);
@@ -465,11 +477,12 @@ template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_ke
 		if (TOL && pending) {
 			/* the stop test of pass p-1: one 16-byte polling load per packet; published before that pass's y, so it is there */
 			const unsigned cq = (unsigned)((p - 1) / a.check_every) + 1u;
+			unsigned spins = 0;
 			for (int x = tid; x < 3 * (int)G; x += SY_CONS) {
 				const uint4 *src = cpk4 + (size_t)(cq & 1u) * G * 3 + x;
 				uint4 v = ld_pair_raw(src);
 				while (v.y != cq || v.w != cq) {
-					__nanosleep(20);
+					spin_pause(spins);
 					v = ld_pair_raw(src);
 				}
 				chk_s[x / 3][2 * (x % 3)] = __uint_as_float(v.x);
