@@ -51,8 +51,6 @@
 #define SY_FLUSH_COST 1.7
 #define SY_RC 6                     /* per owned row: theta+q-, theta+q+, Fd, slack tolerance, y, previous y */
 #define SY_D 4                      /* units in flight per warp (cp.async groups) */
-#define SY_TPR 4                    /* threads per owned row in the owner phase (64 rows per round) */
-#define SY_OB 18                    /* packets in flight per owner thread */
 #define SY_YB 4                     /* float4 of y in flight per thread */
 
 #ifdef PQP_SYM_DEBUG
@@ -251,8 +249,10 @@ __device__ __noinline__ void sym_fetch_y(float *y_s, const uint2 *pk_in, const i
 		for (int i = 4 * n4 + tid; i < N; i += SY_CONS) y_s[i] = ld_packet(pk_in + i, p);
 }
 
-/* the packets of row i: thread group k of SY_TPR sums terms k, k+SY_TPR, ... in ascending order.  Not inlined (see above). */
-__device__ __noinline__ float2 sym_row_terms(const uint4 *rp_in, const uint4 *cp_in, const int *tab_c0, const int *tab_c1, const int *tab_j0,
+/* the packets of row i: thread group k of SY_TPR sums terms k, k+SY_TPR, ... in ascending order, up to SY_OB polling loads in
+ * flight.  Not inlined (see above).  Two shapes: 4 groups x 64 rows per round (N >= 6144: one round for the ~56 rows of a CTA) and
+ * 8 groups x 32 rows (smaller N: half the terms per thread; measured 6-12% faster at N = 2560..4096, 4% slower at 8192). */
+template <int SY_TPR, int SY_OB> __device__ __noinline__ float2 sym_row_terms(const uint4 *rp_in, const uint4 *cp_in, const int *tab_c0, const int *tab_c1, const int *tab_j0,
 					      int nb, int maxseg, int i, int k, uint32_t ep)
 {
 	float num = 0.0f, den = 0.0f;
@@ -338,7 +338,7 @@ struct SymGeom {
  * order, so all decide alike.  A converged run leaves with y_p (each owner keeps the previous value of its rows): bit for bit
  * what the fixed-count solve returns at the reported count.
  */
-template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_args a, const SymGeom g)
+template <bool TOL, int SY_TPR> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_args a, const SymGeom g)
 {
 	__shared__ float chk_s[TOL ? 160 : 1][6];
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -654,13 +654,13 @@ template <bool TOL> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_ke
 			if (gb + tid < nrows && !is_last) st_packet(pk_out + r0 + gb + tid, 1.0f, (uint32_t)(p + 1));
 		if (!SY_DBG)
 		/* lanes along consecutive rows (their packets are contiguous: a warp-wide load touches 4-5 lines, not 32 -- with a thread
-		 * group per row the phase cost one cycle per packet, 5000 cycles), four thread groups over the terms of a row */
+		 * group per row the phase cost one cycle per packet, 5000 cycles), SY_TPR thread groups over the terms of a row */
 		for (int gb = 0; gb < nrows; gb += SY_CONS / SY_TPR) {
 			const int rr = gb + tid % (SY_CONS / SY_TPR), k = tid / (SY_CONS / SY_TPR);
 			const bool valid = rr < nrows;
 			float num = 0.0f, den = 0.0f;
 			if (valid) {
-				const float2 nd = sym_row_terms(rp_in, cp_in, tab_c0, tab_c1, tab_j0, nb, g.maxseg, r0 + rr, k, ep);
+				const float2 nd = sym_row_terms<SY_TPR, (SY_TPR == 8 ? 9 : 18)>(rp_in, cp_in, tab_c0, tab_c1, tab_j0, nb, g.maxseg, r0 + rr, k, ep);
 				num = nd.x;
 				den = nd.y;
 			}
@@ -957,7 +957,9 @@ cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, 
 	if (e == cudaSuccess) e = cudaMemsetAsync(a->barrier, 0, sizeof(unsigned), s);
 	if (e != cudaSuccess) return e;
 	const size_t smem = sym_smem_bytes(g.nb, g.rows_max, g.resident);
-	const void *fn = a->iters > 0 ? (const void *)gemv_sym_kernel<false> : (const void *)gemv_sym_kernel<true>;
+	const bool wide = a->N >= 6144; /* owner phase: 4 thread groups x 64 rows per round, else 8 x 32 */
+	const void *fn = a->iters > 0 ? (wide ? (const void *)gemv_sym_kernel<false, 4> : (const void *)gemv_sym_kernel<false, 8>)
+				      : (wide ? (const void *)gemv_sym_kernel<true, 4> : (const void *)gemv_sym_kernel<true, 8>);
 	if (a->iters <= 0) e = cudaMemsetAsync(a->partials, 0, (size_t)2 * a->grid * 3 * sizeof(uint4), s); /* check packets: epoch 0 = none */
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
