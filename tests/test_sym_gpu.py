@@ -191,3 +191,24 @@ def test_sym_several_right_hand_sides_in_one_call(pqp):
             Yb, _, stb = s.solve(Fd=Fd[b], iters=20)
             assert np.array_equal(Y[b], Yb[0]), b
             np.testing.assert_allclose(st["Jd"][b], stb["Jd"][0], rtol=1e-6)
+
+
+def test_sym_random_sizes_against_the_full_matrix_loop(pqp):
+    """Indexing stress: random generator instances (N in 2369..9000, ragged M, random update counts) through the
+    upper-triangle loop and through the full-matrix loop: same y to rounding, same dual cost, same bits from run to run
+    (tools/sym_stress.py runs a longer list)."""
+    rng = np.random.default_rng(2)
+    for t in range(8):
+        N = int(rng.integers(2369, 9000))
+        M = int(rng.integers(max(8, N // 6), N // 2))
+        K = int(rng.integers(3, 40))
+        prob, d = pqp.generate_testproblem(500 + t, M, N)
+        with pqp.Solver(d, prob) as s:
+            Y, _, st = s.solve(iters=K)
+            assert s.last_kernel.startswith("gemv_sym"), (N, M, s.last_kernel)
+            Y2, _, _ = s.solve(iters=K)
+            assert np.array_equal(Y, Y2), (N, M, K)
+        with pqp.Solver(d, prob, exploit_symmetry=0) as s:
+            Yf, _, stf = s.solve(iters=K)
+        assert np.all(np.isfinite(Y)) and relerr(Y[0], Yf[0]) <= 2e-5, (N, M, K, relerr(Y[0], Yf[0]))
+        np.testing.assert_allclose(st["Jd"][0], stf["Jd"][0], rtol=1e-5)
