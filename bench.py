@@ -14,7 +14,8 @@ Workloads (BASELINE.json configs):
                 a step is one batch solve of I updates; problems shard over ranks with no collective in the loop
                 and one NCCL all-gather of U at the end of every step (inside the timed region).
   c5            the same shapes, 2^20 states IN TOTAL sharded contiguously over the ranks (strong scaling; BASELINE config 5).
-The c3 line also carries the c4 numbers under "batched" so one default run reports both headline metrics.
+The c3 line also carries the c4 numbers under "batched" and the c2 numbers under "onchip", so one default run reports every
+single-GPU config of BASELINE.json.
 
 value    whole-job throughput with inputs resident in HBM (PQP iterations/s for c2/c3, QP solves/s for c4).
 e2e      the same through the C ABI with host buffers: pinned-host Fd/X -> device, solve, Y/U -> host, every step.
@@ -469,6 +470,40 @@ def run_ours(args, w, rank, world, local_rank):
                                           "sample": f"5000 updates of one N={d.N} problem in {dt:.1f} s, scaled to {args.iters} updates/solve"}
         else:
             result["batched"] = batched
+
+    if args.workload == "c3" and not args.no_batched:
+        # the n=1024 single-problem config (BASELINE config 2) rides along: on-chip resident, exchange-latency bound, a few ms
+        w2 = WORKLOADS["c2"]
+        prob2, d2 = pqp.generate_testproblem(w2["seed"], w2["M"], w2["N"])
+        s2 = pqp.Solver(d2, prob2, device=local_rank)
+        s2.solve(iters=1, status=False)
+        Fd2, _ = s2.linear_terms(1)
+        Fd2_dev = torch.from_numpy(Fd2[0]).cuda()
+        Y2_dev = torch.empty(w2["N"], dtype=torch.float32, device="cuda")
+        Fd2_pin = torch.from_numpy(Fd2[0].copy()).pin_memory()
+        Y2_pin = torch.empty(w2["N"], dtype=torch.float32).pin_memory()
+        st2 = np.zeros(1, pqp.STATUS_DTYPE)
+
+        def step2_dev():
+            rc = pqp.lib().pqp_solve_dual(s2.handle, pqp._as_ptr(Fd2_dev.data_ptr()), 1, args.iters, None, pqp._as_ptr(Y2_dev.data_ptr()), None)
+            if rc:
+                raise pqp.PQPError(rc, "pqp_solve_dual")
+
+        def step2_e2e():
+            rc = pqp.lib().pqp_solve_dual(s2.handle, pqp._as_ptr(Fd2_pin.data_ptr()), 1, args.iters, None, pqp._as_ptr(Y2_pin.data_ptr()),
+                                          pqp._as_ptr(st2))
+            if rc:
+                raise pqp.PQPError(rc, "pqp_solve_dual")
+
+        ms2, _ = timed(step2_dev, s2.stream)
+        ms2e, _ = timed(step2_e2e, s2.stream)
+        result["onchip"] = {"metric": "pqp_iters_per_sec", "unit": "iterations/s", "value": world * args.iters * args.steps / (ms2 * 1e-3),
+                            "ms_per_step": ms2 / args.steps,
+                            "e2e": {"value": world * args.iters * args.steps / (ms2e * 1e-3), "unit": "iterations/s",
+                                    "h2d_bytes_per_step": 4 * w2["N"], "d2h_bytes_per_step": 4 * w2["N"] + st2.itemsize},
+                            "config": {"workload": "c2", "N": w2["N"], "M": w2["M"], "seed": w2["seed"], "iters_per_step": args.iters,
+                                       "kernel": s2.last_kernel, "note": "Q (4 MB) lives in registers across 64 SMs: exchange-latency bound, no HBM roofline"}}
+        s2.close()
 
     if dist is not None:
         dist.barrier()
