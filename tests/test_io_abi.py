@@ -121,6 +121,15 @@ def test_no_cpu_fallback(pqp):
     assert e.value.code == -2
     with pytest.raises(pqp.PQPError):
         pqp.Solver(Qd=np.eye(4, dtype=np.float32))
+    # the stand-alone device entry points refuse as well
+    I4 = np.eye(4, dtype=np.float32)
+    v4 = np.ones(4, np.float32)
+    with pytest.raises(pqp.PQPError) as e:
+        pqp.update_y2(v4, I4, I4, v4, v4)
+    assert e.value.code == -2
+    with pytest.raises(pqp.PQPError) as e:
+        pqp.matmul(I4, I4)
+    assert e.value.code == -2
 
 
 def test_product_never_references_the_oracle():
