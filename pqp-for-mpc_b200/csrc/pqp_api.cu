@@ -538,7 +538,7 @@ static int ensure_sym(pqp_handle *h)
 	cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, h->device);
 	const int streamed = umax - pl.resident > 0 ? umax - pl.resident : 0;
 	const double unit_bytes = 64.0 * 128.0 * 4.0;
-	double frac = 0.6;
+	double frac = 0.5; /* measured at N=8192 (29 units per CTA): 10-16 units per CTA evict_last is a plateau (19.6 us/update); 0: 25.2, 8: 20.5, 18: 20.1, 28: 25.9 */
 	if ((e = getenv("PQP_SYM_PIN_FRAC"))) frac = atof(e);
 	pl.pinned = streamed;
 	if ((double)streamed * G * unit_bytes > 0.8 * (double)l2_bytes) pl.pinned = (int)(frac * (double)l2_bytes / ((double)G * unit_bytes));
