@@ -1,5 +1,5 @@
 """Timing experiments on the upper-triangle loop (results invalid under PQP_SYM_DBG != 0): python tools/sym_dbg.py N [dbg ...]
-The switches exist only in a library built with -DPQP_SYM_DEBUG (make NVCCFLAGS+=-DPQP_SYM_DEBUG); PQP_SYM_PROF=1 works in any build."""
+The switches exist only in a library built with -DPQP_SYM_DEBUG (make EXTRA=-DPQP_SYM_DEBUG); PQP_SYM_PROF=1 works in any build."""
 import os, sys
 sys.path.insert(0, "/root/repo")
 import pqp_for_mpc_b200 as pqp
