@@ -536,7 +536,18 @@ static int ensure_sym(pqp_handle *h)
 	 * fraction of L2 spread evenly over the CTAs */
 	int l2_bytes = 0;
 	cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, h->device);
-	const int streamed = umax - pl.resident > 0 ? umax - pl.resident : 0;
+	/* eight more units per CTA can live in the SM's tensor memory (256 KB, otherwise idle in this loop).  Measured (B200): a unit read
+	 * back from tensor memory costs about what a streamed unit costs once the copy pipelines are in steady state, so parking pays
+	 * where it takes a large share of the traffic away -- N=4096 (everything on chip) 7.6 -> 6.9 us/update, N=6144 (8 of 15
+	 * parked) 14.9 -> 13.0 -- and not at N=8192 (8 of 28: 19.3 -> 19.4-19.7): used while at least half of the units outside shared
+	 * memory fit */
+	pl.tmem = (umax - pl.resident <= 16) ? 8 : 0;
+	if ((e = getenv("PQP_SYM_TMEM"))) {
+		int v = atoi(e);
+		if (v >= 0 && v <= 8) pl.tmem = v;
+	}
+	if (pl.tmem > umax - pl.resident) pl.tmem = umax - pl.resident > 0 ? umax - pl.resident : 0;
+	const int streamed = umax - pl.resident - pl.tmem > 0 ? umax - pl.resident - pl.tmem : 0;
 	const double unit_bytes = 64.0 * 128.0 * 4.0;
 	double frac = 0.5; /* measured at N=8192 (29 units per CTA): 10-16 units per CTA evict_last is a plateau (19.6 us/update); 0: 25.2, 8: 20.5, 18: 20.1, 28: 25.9 */
 	if ((e = getenv("PQP_SYM_PIN_FRAC"))) frac = atof(e);
@@ -572,8 +583,8 @@ static int ensure_sym(pqp_handle *h)
 	CK(ce);
 	h->launches++;
 	if (getenv("PQP_VERBOSE"))
-		fprintf(stderr, "pqp: gemv_sym N=%d grid=%d units=%d (%d per CTA) stages=%d resident=%d pinned=%d maxseg=%d\n", N, G, pl.U, umax,
-			pl.stages, pl.resident, pl.pinned, pl.maxseg);
+		fprintf(stderr, "pqp: gemv_sym N=%d grid=%d units=%d (%d per CTA) stages=%d resident=%d tmem=%d pinned=%d maxseg=%d\n", N, G, pl.U, umax,
+			pl.stages, pl.resident, pl.tmem, pl.pinned, pl.maxseg);
 	h->sym_state = 1;
 	return PQP_OK;
 }
@@ -660,7 +671,7 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		int rc = ensure_sym(h);
 		if (rc) return rc;
 		if (h->sym_state == 1) {
-			const int all_res = h->sym.resident >= (h->sym.U + h->gemv_grid - 1) / h->gemv_grid;
+			const int all_res = h->sym.resident + h->sym.tmem >= (h->sym.U + h->gemv_grid - 1) / h->gemv_grid;
 			h->last_kernel = iters > 0 ? (all_res ? "gemv_sym_resident" : "gemv_sym_stream") : (all_res ? "gemv_sym_resident_tol" : "gemv_sym_stream_tol");
 			CK(pqp_launch_gemv_sym(&a, &h->sym, h->pk0, h->pk1, h->stream));
 			h->launches++;

@@ -52,6 +52,7 @@
 #define SY_RC 6                     /* per owned row: theta+q-, theta+q+, Fd, slack tolerance, y, previous y */
 #define SY_D 4                      /* units in flight per warp (cp.async groups) */
 #define SY_YB 4                     /* float4 of y in flight per thread */
+#define SY_UMAX 512                 /* most units per CTA the tensor-memory tables cover (N = 16384 on 148 CTAs: 113) */
 
 #ifdef PQP_SYM_DEBUG
 #define SY_DBG g.dbg_
@@ -137,6 +138,45 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint64
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+/*
+ * Tensor memory as a second on-chip store for units.  The loop has no tensor-core work, so the SM's 256 KB of TMEM (128 lanes x
+ * 512 columns x 32 bit) would sit idle; it holds eight more 32 KB units per SM for the whole launch (37 MB over 148 SMs that
+ * neither HBM nor L2 has to deliver again on every update).  A warp reaches lanes 32*(warp%4)..+31 only: warps 0-3 use columns
+ * [64u, 64u+32) of unit slot u, warps 4-7 columns [64u+32, 64u+64); a thread's 32 columns are its eight float4 of the unit.
+ */
+/* sixteen columns -> four float4; the registers are valid only after tmem_ld_wait() */
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float4 &q0, float4 &q1, float4 &q2, float4 &q3)
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+		     : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w), "=f"(q2.x), "=f"(q2.y), "=f"(q2.z),
+		       "=f"(q2.w), "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w)
+		     : "r"(taddr));
+}
+/* the wait names the registers it makes valid, so that no use of them can be scheduled ahead of it */
+__device__ __forceinline__ void tmem_ld_wait(float4 &q0, float4 &q1, float4 &q2, float4 &q3)
+{
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+		     : "+f"(q0.x), "+f"(q0.y), "+f"(q0.z), "+f"(q0.w), "+f"(q1.x), "+f"(q1.y), "+f"(q1.z), "+f"(q1.w), "+f"(q2.x), "+f"(q2.y), "+f"(q2.z),
+		       "+f"(q2.w), "+f"(q3.x), "+f"(q3.y), "+f"(q3.z), "+f"(q3.w));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float4 (&q)[8])
+{
+	uint32_t r[32];
+	const int order[8] = { 0, 1, 4, 5, 2, 3, 6, 7 }; /* the two halves the unit loop consumes one after the other */
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		const float4 v = q[order[k]];
+		r[4 * k] = __float_as_uint(v.x); r[4 * k + 1] = __float_as_uint(v.y);
+		r[4 * k + 2] = __float_as_uint(v.z); r[4 * k + 3] = __float_as_uint(v.w);
+	}
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+		     "%29,%30,%31,%32};" ::"r"(taddr),
+		     "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+		     "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+		     "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+		     : "memory");
+}
 
 /* packed fp32 pairs (FFMA2) */
 __device__ __forceinline__ u64 pk2(float lo, float hi)
@@ -317,6 +357,7 @@ struct SymGeom {
 	uint2 *pk0, *pk1;      /* y packets [ldq], epochs preset to 0xFFFFFFFF */
 	uint4 *rowpart;        /* [2][nT][128] row-direction packets, zeroed before launch (epoch 0 = none) */
 	uint4 *colpart;        /* [2][G][maxseg][128] column-direction packets */
+	int tmem_units;        /* units per CTA parked in tensor memory for the whole launch (0: tensor memory not allocated) */
 	int dbg_;              /* timing experiments only (PQP_SYM_DBG): 1 no arithmetic, 2 no row packets, 4 no unit loads, 8 no column flush; results invalid */
 	long long *prof;       /* debug (PQP_SYM_PROF=1): [G][4] cycles in y fetch / units / owner phase, else NULL */
 };
@@ -338,9 +379,10 @@ struct SymGeom {
  * order, so all decide alike.  A converged run leaves with y_p (each owner keeps the previous value of its rows): bit for bit
  * what the fixed-count solve returns at the reported count.
  */
-template <bool TOL, int SY_TPR> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_args a, const SymGeom g)
+template <bool TOL, int SY_TPR, bool TMU> __global__ void __launch_bounds__(SY_THREADS, 1) gemv_sym_kernel(const pqp_gemv_args a, const SymGeom g)
 {
 	__shared__ float chk_s[TOL ? 160 : 1][6];
+	__shared__ uint32_t tmem_base_s;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 	const int N = a.N, nb = g.nb;
@@ -350,6 +392,8 @@ template <bool TOL, int SY_TPR> __global__ void __launch_bounds__(SY_THREADS, 1)
 	const int nrows = r1 - r0;
 	const int u0 = g.cta_u0[cta], nU = g.cta_u0[cta + 1] - u0;
 	const int R = min(g.resident, nU);
+	const int L = nU - R;                /* units of the range outside shared memory ... */
+	const int TM = TMU ? min(g.tmem_units, L) : 0; /* ... of which TM, spread evenly (so that the copy pipeline keeps running while they are worked on), live in tensor memory */
 	const size_t nT = (size_t)nb * (nb + 1) / 2;
 
 	float *ring = reinterpret_cast<float *>(smem_raw);
@@ -367,12 +411,16 @@ template <bool TOL, int SY_TPR> __global__ void __launch_bounds__(SY_THREADS, 1)
 	 * the next y: the ping-pong packet buffers stay safe without a global barrier (a CTA polling rows it does not feed could be
 	 * overtaken by two passes and spin on an epoch that is gone).  The y of its OWN rows never leaves the CTA (rowc[5*rr+4]). */
 
+	/* TMU: ukind[t] = column of unit t in tensor memory or -1; snext[i] = the i-th unit of the range that is streamed */
+	short *ukind = reinterpret_cast<short *>(need + 1 + nb);
+	short *snext = ukind + SY_UMAX;
+
 	const int passes = (TOL ? a.max_iters : a.iters) + 1; /* updates + one evaluation pass */
 	uint4 *cpk4 = reinterpret_cast<uint4 *>(a.partials); /* TOL: [2][G][3] check packets */
 	float *fin = a.partials + (TOL ? (size_t)2 * G * 12 : 0); /* final per-CTA slots, clear of the check packets */
 
 	/* ---- this warp's copy pipeline ---- */
-	const int T = nU - R; /* streamed units per pass */
+	const int T = nU - R - TM; /* streamed units per pass */
 	const float *mine = g.units + (size_t)u0 * SY_UNIT + (warp * 256 + lane) * 4;
 	const uint32_t ring_w = smem_u32(ring) + (uint32_t)(warp * 256 + lane) * 16u;
 	const uint64_t pol_keep = make_policy(g.pol_keep), pol_stream = make_policy(g.pol_stream);
@@ -383,6 +431,7 @@ template <bool TOL, int SY_TPR> __global__ void __launch_bounds__(SY_THREADS, 1)
 	int iu = 0, islot = 0, pacc = 0;
 	auto request = [&]() {
 		if (left > 0) {
+			if (TMU) rsrc = mine + (size_t)snext[iu] * SY_UNIT; /* the units in tensor memory are not in this list */
 			/* Pn of every T units are fetched evict_last, spread evenly through the range so L2 hits and HBM misses overlap in time */
 			pacc += Pn;
 			const bool keep = pacc >= T;
@@ -405,6 +454,15 @@ template <bool TOL, int SY_TPR> __global__ void __launch_bounds__(SY_THREADS, 1)
 		}
 		cp_async_commit(); /* one group per call, empty or not: the group arithmetic below stays uniform */
 	};
+	if (TMU) {
+		for (int x = tid; x < L; x += SY_CONS) {
+			const int before = (int)(((long long)x * TM) / L); /* units in tensor memory among the first x */
+			const bool here = (int)(((long long)(x + 1) * TM) / L) != before;
+			ukind[R + x] = here ? (short)(64 * before) : (short)-1;
+			if (!here) snext[x - before] = (short)(R + x);
+		}
+		consumer_sync();
+	}
 	{
 		const uint32_t rdst = smem_u32(resid) + (uint32_t)(warp * 256 + lane) * 16u;
 		for (int t = 0; t < R; t++)
@@ -415,6 +473,27 @@ template <bool TOL, int SY_TPR> __global__ void __launch_bounds__(SY_THREADS, 1)
 		cp_async_wait<SY_D - 1>(); /* the resident units have landed */
 	}
 	int cslot = 0; /* ring slot of the next streamed unit to consume */
+	uint32_t tm_mine = 0; /* this thread's lane / column origin in tensor memory */
+	if (TMU) {
+		if (warp == 0) {
+			asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+		}
+		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+		consumer_sync();
+		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+		tm_mine = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 32);
+		for (int x = 0; x < L; x++) {
+			const int col = ukind[R + x];
+			if (col < 0) continue;
+			const float4 *src = reinterpret_cast<const float4 *>(mine + (size_t)(R + x) * SY_UNIT);
+			float4 q[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) q[k] = __ldcs(src + 32 * k);
+			tmem_st32(tm_mine + (uint32_t)col, q);
+		}
+		asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+	}
 
 	/* per-row constants of the rows this CTA finishes: theta_i + max(-+q_ii, 0) as the reference forms Q-+ + theta in fp32
 	 * (computeQdn_theta / computeQdp_theta, PQP_CPU.c:524-537), F_i, and the slack tolerance */
@@ -547,37 +626,65 @@ template <bool TOL, int SY_TPR> __global__ void __launch_bounds__(SY_THREADS, 1)
 					for (int k = 0; k < 8; k++) cn[k] = cd[k] = 0ull; /* +0.0f pairs */
 					fresh = false;
 				}
-				const float4 *up;
+				const float4 *up = nullptr;
+				bool in_tm = false;
+				uint32_t tm_col = 0;
 				if (t < R) {
 					up = reinterpret_cast<const float4 *>(resid + (size_t)t * SY_UNIT) + warp * 256 + lane;
 				} else {
-					cp_async_wait<SY_D - 2>(); /* all but the newest SY_D-2 groups: this unit's slab is in */
-					up = reinterpret_cast<const float4 *>(ring + (size_t)cslot * SY_UNIT) + warp * 256 + lane;
-					if (++cslot == SY_D) cslot = 0;
-				}
-				float4 q[8];
-				if (!(SY_DBG & 4)) {
-#pragma unroll
-					for (int k = 0; k < 8; k++) q[k] = up[32 * k];
-				} else {
-#pragma unroll
-					for (int k = 0; k < 8; k++) q[k] = make_float4(1.f, -1.f, 2.f, -2.f);
+					const int col = TMU ? (int)ukind[t] : -1;
+					in_tm = TMU && col >= 0;
+					if (in_tm) {
+						tm_col = (uint32_t)col;
+					} else {
+						cp_async_wait<SY_D - 2>(); /* all but the newest SY_D-2 groups: this unit's slab is in */
+						up = reinterpret_cast<const float4 *>(ring + (size_t)cslot * SY_UNIT) + warp * 256 + lane;
+						if (++cslot == SY_D) cslot = 0;
+					}
 				}
 				const float *yip = y_s + I * SY_BS + h * SY_UR + 8 * warp + la;
 				const float yi0 = yip[0], yi1 = yip[4];
 				u64 rn0 = 0, rd0 = 0, rn1 = 0, rd1 = 0;
-				if (SY_DBG & 1) {
-					rn0 = pk2(q[0].x + q[1].y + q[2].z + q[3].w, yi0);
-					rn1 = pk2(q[4].x + q[5].y + q[6].z + q[7].w, yi1);
-				} else {
+				/* two complete copies of the unit's arithmetic: a unit from tensor memory waits for its second half in the middle,
+				 * and a wait inside the block the other units run through would cut that block's instruction schedule in two */
+				if (TMU && in_tm) {
+					float4 q[8];
+					tmem_ld16(tm_mine + tm_col, q[0], q[1], q[4], q[5]);
+					tmem_ld_wait(q[0], q[1], q[4], q[5]);
+					tmem_ld16(tm_mine + tm_col + 16, q[2], q[3], q[6], q[7]); /* in flight behind the first half's arithmetic */
 #pragma unroll
-					for (int k = 0; k < 4; k++) {
+					for (int k = 0; k < 2; k++) {
 						sym_row(q[k], yj[2 * k], yj[2 * k + 1], yi0, neg1, rn0, rd0, cn[2 * k], cn[2 * k + 1], cd[2 * k], cd[2 * k + 1]);
 						sym_row(q[4 + k], yj[2 * k], yj[2 * k + 1], yi1, neg1, rn1, rd1, cn[2 * k], cn[2 * k + 1], cd[2 * k], cd[2 * k + 1]);
 					}
+					tmem_ld_wait(q[2], q[3], q[6], q[7]);
+#pragma unroll
+					for (int k = 2; k < 4; k++) {
+						sym_row(q[k], yj[2 * k], yj[2 * k + 1], yi0, neg1, rn0, rd0, cn[2 * k], cn[2 * k + 1], cd[2 * k], cd[2 * k + 1]);
+						sym_row(q[4 + k], yj[2 * k], yj[2 * k + 1], yi1, neg1, rn1, rd1, cn[2 * k], cn[2 * k + 1], cd[2 * k], cd[2 * k + 1]);
+					}
+				} else {
+					float4 q[8];
+					if (!(SY_DBG & 4)) {
+#pragma unroll
+						for (int k = 0; k < 8; k++) q[k] = up[32 * k];
+					} else {
+#pragma unroll
+						for (int k = 0; k < 8; k++) q[k] = make_float4(1.f, -1.f, 2.f, -2.f);
+					}
+					if (SY_DBG & 1) {
+						rn0 = pk2(q[0].x + q[1].y + q[2].z + q[3].w, yi0);
+						rn1 = pk2(q[4].x + q[5].y + q[6].z + q[7].w, yi1);
+					} else {
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							sym_row(q[k], yj[2 * k], yj[2 * k + 1], yi0, neg1, rn0, rd0, cn[2 * k], cn[2 * k + 1], cd[2 * k], cd[2 * k + 1]);
+							sym_row(q[4 + k], yj[2 * k], yj[2 * k + 1], yi1, neg1, rn1, rd1, cn[2 * k], cn[2 * k + 1], cd[2 * k], cd[2 * k + 1]);
+						}
+					}
 				}
 				/* the slab is consumed (its values feed the sums above): request the one SY_D-1 units ahead into the freed slot */
-				if (t >= R) request();
+				if (t >= R && !in_tm) request();
 				/* the row sums of the PREVIOUS unit are reduced and stored here, next to this unit's arithmetic, so that a warp
 				 * never sits on its own shuffle/store chain */
 				if (pend && !(SY_DBG & 2)) row_finish(pn0, pn1, pd0, pd1, pdst, ep, lane);
@@ -776,6 +883,11 @@ template <bool TOL, int SY_TPR> __global__ void __launch_bounds__(SY_THREADS, 1)
 		}
 	}
 	cp_async_wait<0>();
+	if (TMU) {
+		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+		consumer_sync();
+		if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base_s) : "memory");
+	}
 }
 
 /* ---- one-time kernels: symmetry test and the unit array ---------------------------------------------------------------- */
@@ -905,7 +1017,7 @@ extern "C" int pqp_internal_sym_tables(int N, int G, int *cta_u0, int *cta_j0, i
 static size_t sym_smem_bytes(int nb, int rows_max, int resident)
 {
 	return sizeof(float) * ((size_t)(SY_D + resident) * SY_UNIT + (size_t)nb * SY_BS + 4 * SY_WARPS * SY_BS + 2 * SY_CONS + SY_RC * (size_t)rows_max +
-				SY_WARPS * 8) + sizeof(int) * (3 * (size_t)nb + 1 + 512) + 128; /* + the tables (grid <= 512) */
+				SY_WARPS * 8) + sizeof(int) * (3 * (size_t)nb + 1 + 512) + 2 * SY_UMAX * sizeof(short) + 128; /* + the tables (grid <= 512) */
 }
 
 /* residency for the shared-memory budget (the ring is SY_D units deep); 0 when the shape does not fit */
@@ -916,7 +1028,7 @@ int pqp_gemv_sym_plan(int N, int grid, size_t smem_budget, int *stages, int *res
 	if (U < grid || N < 4 * SY_BS) return 0;
 	const int rows_max = (N + grid - 1) / grid + 1;
 	const int umax = (U + grid - 1) / grid;
-	const size_t fixed = sym_smem_bytes(nb, rows_max, 0) + 64;
+	const size_t fixed = sym_smem_bytes(nb, rows_max, 0) + 4096; /* + the kernel's static shared memory (stop-test values, TMEM base) */
 	if (fixed > smem_budget) return 0;
 	int res = (int)((smem_budget - fixed) / ((size_t)SY_UNIT * 4));
 	if (res > umax) res = umax;
@@ -931,7 +1043,7 @@ cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, 
 	g.units = pl->units;
 	g.cta_u0 = pl->cta_u0; g.cta_j0 = pl->cta_j0; g.strip_c0 = pl->strip_c0; g.strip_c1 = pl->strip_c1;
 	g.nb = pl->nb; g.U = pl->U; g.maxseg = pl->maxseg;
-	g.resident = pl->resident; g.pinned = pl->pinned;
+	g.resident = pl->resident; g.pinned = pl->pinned; g.tmem_units = pl->tmem;
 	g.rows_max = (a->N + a->grid - 1) / a->grid + 1;
 	g.pol_keep = 2;
 	g.pol_stream = 1;
@@ -958,8 +1070,13 @@ cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, 
 	if (e != cudaSuccess) return e;
 	const size_t smem = sym_smem_bytes(g.nb, g.rows_max, g.resident);
 	const bool wide = a->N >= 6144; /* owner phase: 4 thread groups x 64 rows per round, else 8 x 32 */
-	const void *fn = a->iters > 0 ? (wide ? (const void *)gemv_sym_kernel<false, 4> : (const void *)gemv_sym_kernel<false, 8>)
-				      : (wide ? (const void *)gemv_sym_kernel<true, 4> : (const void *)gemv_sym_kernel<true, 8>);
+	const int umax_cta = (pl->U + a->grid - 1) / a->grid + 2;
+	if (2 * umax_cta > SY_UMAX) g.tmem_units = 0; /* the cost-balanced ranges differ by a few units from the mean */
+	const bool tmu = g.tmem_units > 0;
+	const void *fn = a->iters > 0 ? (wide ? (tmu ? (const void *)gemv_sym_kernel<false, 4, true> : (const void *)gemv_sym_kernel<false, 4, false>)
+					      : (tmu ? (const void *)gemv_sym_kernel<false, 8, true> : (const void *)gemv_sym_kernel<false, 8, false>))
+				      : (wide ? (tmu ? (const void *)gemv_sym_kernel<true, 4, true> : (const void *)gemv_sym_kernel<true, 4, false>)
+					      : (tmu ? (const void *)gemv_sym_kernel<true, 8, true> : (const void *)gemv_sym_kernel<true, 8, false>));
 	if (a->iters <= 0) e = cudaMemsetAsync(a->partials, 0, (size_t)2 * a->grid * 3 * sizeof(uint4), s); /* check packets: epoch 0 = none */
 	if (e != cudaSuccess) return e;
 	e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -98,6 +98,7 @@ cudaError_t pqp_launch_gemv_small(const pqp_gemv_args *a, int wpr, int cpt, void
 typedef struct pqp_sym_plan {
 	int nb, U, maxseg;           /* 128-wide blocks, 64x128 units of the upper triangle, most strips one CTA touches */
 	int stages, resident, pinned;
+	int tmem;                    /* units per CTA parked in tensor memory (0..8) */
 	float *units;                /* device [U][64][128] */
 	int *cta_u0, *cta_j0, *strip_c0, *strip_c1; /* device tables (pqp_gemv_sym_tables) */
 	void *rowpart, *colpart;     /* device packet arrays */

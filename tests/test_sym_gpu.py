@@ -212,3 +212,27 @@ def test_sym_random_sizes_against_the_full_matrix_loop(pqp):
             Yf, _, stf = s.solve(iters=K)
         assert np.all(np.isfinite(Y)) and relerr(Y[0], Yf[0]) <= 2e-5, (N, M, K, relerr(Y[0], Yf[0]))
         np.testing.assert_allclose(st["Jd"][0], stf["Jd"][0], rtol=1e-5)
+
+
+def test_sym_units_in_tensor_memory_change_nothing(pqp):
+    """Up to eight units per SM are parked in tensor memory (PQP_SYM_TMEM; by default below N ~ 6800) instead of being streamed: where a unit is
+    kept does not enter the arithmetic, so 0, 3 and 8 parked units must give the same bits -- fixed count and run to tolerance,
+    at a size that is fully on chip with them (N = 3001), one that is half streamed (6100) and the C3 size."""
+    import os
+    for N, M, K in ((3001, 700, 30), (6100, 1500, 12), (8192, 2048, 6)):
+        prob, d = pqp.generate_testproblem(77, M, N)
+        got = {}
+        for tm in ("0", "3", "8"):
+            os.environ["PQP_SYM_TMEM"] = tm
+            try:
+                with pqp.Solver(d, prob, check_every=4, max_iters=K + 3) as s:  # the stop test is evaluated, never met: ends at the cap
+                    Y, _, st = s.solve(iters=K)
+                    assert s.last_kernel.startswith("gemv_sym"), (N, tm, s.last_kernel)
+                    Yt, _, stt = s.solve(iters=0)
+                    got[tm] = (Y.copy(), st["Jd"][0], Yt.copy(), int(stt["iters"][0]))
+            finally:
+                os.environ.pop("PQP_SYM_TMEM", None)
+        for tm in ("3", "8"):
+            assert np.array_equal(got["0"][0], got[tm][0]), (N, tm)
+            assert got["0"][1] == got[tm][1], (N, tm)
+            assert np.array_equal(got["0"][2], got[tm][2]) and got["0"][3] == got[tm][3], (N, tm)
