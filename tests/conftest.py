@@ -61,6 +61,17 @@ def gold_random():
     return np.load(os.path.join(GOLDEN, "golden_random.npz"))
 
 
+@pytest.fixture(scope="session")
+def gold_testfiles():
+    """The reference's larger generated instances test1.txt / test3.txt (tests/golden/make_golden_testfiles.py)."""
+    return np.load(os.path.join(GOLDEN, "golden_testfiles.npz"))
+
+
+def problem_from_testfile(g, name):
+    return dict(Qp_inv=np.diag(g[f"{name}_Qp_inv_diag"]).astype(np.float32), Fp=g[f"{name}_Fp"], Kp=g[f"{name}_Kp"],
+                Gp=g[f"{name}_Gp"].astype(np.float32), Mp0=float(g[f"{name}_Mp0"]))
+
+
 def relerr(a, b):
     """normwise relative error ||a-b||inf / ||b||inf (the tolerance metric of DESIGN.md)"""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)

@@ -85,6 +85,24 @@ def test_random_matches_golden_bit_for_bit(oracle32, oracle64, gold_random, seed
     assert np.array_equal(Y64, g[f"{t}_Y64"])
 
 
+@pytest.mark.parametrize("name", ["test1", "test3"])
+def test_reference_testfiles_match_golden_bit_for_bit(oracle32, oracle64, gold_testfiles, name):
+    """testing/sample test/test1.txt (M=500, N=1500) and test3.txt (M=800, N=1200) of the reference: the restatement against
+    what the unmodified reference makes of them (100 updates)."""
+    from conftest import problem_from_testfile
+    g = gold_testfiles
+    prob = problem_from_testfile(g, name)
+    Qd, Fd, Md, GQ = oracle32.convert_to_dual(prob["Qp_inv"], prob["Gp"], prob["Kp"], prob["Fp"], prob["Mp0"])
+    assert np.array_equal(Fd, g[f"{name}_Fd"]) and np.array_equal(Qd.sum(1), g[f"{name}_Qd_rowsum"])
+    assert np.array_equal(np.diag(Qd), g[f"{name}_Qd_diag"])
+    K = int(g[f"{name}_K"])
+    Y, th = oracle32.solve_fixed(Qd, Fd, K)
+    assert np.array_equal(th, g[f"{name}_theta"]) and np.array_equal(Y, g[f"{name}_Y"])
+    assert np.array_equal(oracle32.recover_u(Y, prob["Fp"], prob["Gp"], prob["Qp_inv"]), g[f"{name}_U"])
+    Y64, _ = oracle64.solve_fixed(Qd, Fd, K)
+    assert np.array_equal(Y64, g[f"{name}_Y64"])
+
+
 def test_split_matrices_and_single_update(oracle32, gold_random):
     g, t = gold_random, "s101"
     Qd, Fd = g[f"{t}_Qd"], g[f"{t}_Fd"]

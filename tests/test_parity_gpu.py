@@ -143,6 +143,32 @@ def test_reference_generated_file_test2(pqp, gold_random):
         assert np.array_equal(active_set(Y[0]), active_set(g["test2_Y"]))
 
 
+@pytest.mark.parametrize("name", ["test1", "test3"])
+def test_reference_generated_files_test1_test3(pqp, oracle32, gold_testfiles, name):
+    """The reference's larger generated instances (M=500/N=1500 and M=800/N=1200, rank-deficient duals with every constraint
+    active): reference order bit for bit -- dual, theta, y after 100 updates, U --, fast order within the stated tolerance with
+    the same active set, on the register-resident loop these sizes select."""
+    from conftest import problem_from_testfile
+    g = gold_testfiles
+    prob = problem_from_testfile(g, name)
+    M, N, K = int(g[f"{name}_M"]), int(g[f"{name}_N"]), int(g[f"{name}_K"])
+    with pqp.Solver(pqp.dims_plain(M, N), prob, order=pqp.ORDER_STRICT) as s:
+        Qd, th, _ = s.dual()
+        assert np.array_equal(Qd.sum(1), g[f"{name}_Qd_rowsum"]) and np.array_equal(np.diag(Qd), g[f"{name}_Qd_diag"])
+        assert np.array_equal(th, g[f"{name}_theta"])
+        Y, U, _ = s.solve(iters=K, primal=True)
+        Fd, _ = s.linear_terms(1)
+        assert np.array_equal(Fd[0], g[f"{name}_Fd"])
+        assert np.array_equal(Y[0], g[f"{name}_Y"]) and np.array_equal(U[0], g[f"{name}_U"])
+    with pqp.Solver(pqp.dims_plain(M, N), prob) as s:
+        Y, U, st = s.solve(iters=K, primal=True)
+        assert s.last_kernel.startswith("gemv_small"), s.last_kernel
+        check_fast(Y[0], g[f"{name}_Y"], g[f"{name}_Y64"], name)
+        assert np.array_equal(active_set(Y[0]), active_set(g[f"{name}_Y"]))
+        assert np.array_equal(U[0], oracle32.recover_u(Y[0], prob["Fp"], prob["Gp"], prob["Qp_inv"]))
+        assert st["iters"][0] == K
+
+
 def test_warm_start_and_chunking(pqp, gold_random):
     """Y0: K1 updates then K2 more equals K1+K2 in one go (strict: bitwise)."""
     g, t = gold_random, "s103"
