@@ -110,7 +110,9 @@ typedef struct pqp_opts {
 	int exploit_symmetry; /* FAST mode, one problem, fixed count: 1 (default) when the fp32 Qd of the handle is symmetric element
 			       * for element (tested once on the device) the loop reads its upper triangle only -- half the bytes per
 			       * update, same sums in a different order; 0 always read the full matrix.  Never applies to a Qd that is
-			       * not exactly symmetric */
+			       * not exactly symmetric.  pqp_setup (not pqp_setup_dual), FAST order: the Qd it
+			       * builds from Gp Qp_inv Gp' gets one value per pair (Q_ij, Q_ji) -- their mean -- when all pairs agree to
+			       * rounding (1e-5 sqrt(Q_ii Q_jj)), so a dense symmetric Qp_inv also reaches the upper-triangle loop */
 } pqp_opts;
 
 /* Per-problem result of a solve (replaces the printf's of PQP_CPU.c:741,1005-1006). */

@@ -427,6 +427,24 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 		pqp_destroy(h);
 		return PQP_ERR_CUDA;
 	}
+	if (!strict && o.exploit_symmetry) {
+		/* Gp Qp_inv Gp' is symmetric in exact arithmetic; its two fp32 copies of an element are different sums.  One value per
+		 * pair (their mean) when all pairs agree to rounding: then every loop sees a symmetric Qd and the single-problem loop can
+		 * run from the upper triangle.  A Qd whose copies differ by more than rounding (an unsymmetric Qp_inv) is left as computed. */
+		unsigned *bad_dev = NULL, bad = 0;
+		if ((rc = dalloc(&bad_dev, 1))) { pqp_destroy(h); return rc; }
+		e = pqp_launch_sym_mean(h->Q, h->ldq, N, 1e-5f, bad_dev, h->stream);
+		if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, bad_dev, sizeof bad, cudaMemcpyDeviceToHost, h->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+		cudaFree(bad_dev);
+		h->launches += 2;
+		if (e != cudaSuccess) {
+			snprintf(g_cuda_err, sizeof g_cuda_err, "symmetry pass -> %s", cudaGetErrorString(e));
+			pqp_destroy(h);
+			return PQP_ERR_CUDA;
+		}
+		if (getenv("PQP_VERBOSE")) fprintf(stderr, "pqp: setup: %u pairs of Qd differ by more than rounding%s\n", bad, bad ? " (left as computed)" : " (both copies set to their mean)");
+	}
 	if ((rc = finish_setup(h))) { pqp_destroy(h); return rc; }
 	*out = h;
 	return PQP_OK;

@@ -913,6 +913,72 @@ __global__ void sym_check_kernel(const float *Q, int ldq, int N, unsigned *misma
 	if (tx == 0 && bad) atomicAdd(mismatch, bad);
 }
 
+/*
+ * Qd = Gp Qp_inv Gp' built by pqp_setup is symmetric in exact arithmetic whenever Qp_inv is; in fp32 its two copies of an
+ * element are two different sums and differ in the last bits (they do not for the generator's diagonal Qp_inv).  FAST order
+ * already takes Qd from a GEMM whose sums are not the reference's, so it may as well take ONE value per pair: when every pair
+ * agrees to rounding -- |Q_ij - Q_ji| <= tol * sqrt(|Q_ii Q_jj|), the scale of a rounding error of such a product -- both
+ * copies are replaced by their mean.  Pass 1 counts the pairs that do not agree (or are not finite); pass 2 does nothing
+ * unless that count is zero, so an unsymmetric Qp_inv keeps the matrix it produced.  Never applied to a user-supplied Qd.
+ */
+__global__ void sym_near_check_kernel(const float *Q, int ldq, int N, float tol, unsigned *mismatch)
+{
+	__shared__ float tA[32][33], tB[32][33];
+	const int bi = blockIdx.y, bj = blockIdx.x;
+	if (bi > bj) return;
+	const int tx = threadIdx.x, ty = threadIdx.y; /* 32 x 8 */
+	for (int r = ty; r < 32; r += 8) {
+		const int i = bi * 32 + r, j = bj * 32 + tx;
+		tA[r][tx] = (i < N && j < N) ? Q[(size_t)i * ldq + j] : 0.0f;
+		const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+		tB[r][tx] = (i2 < N && j2 < N) ? Q[(size_t)i2 * ldq + j2] : 0.0f;
+	}
+	__syncthreads();
+	unsigned bad = 0;
+	for (int r = ty; r < 32; r += 8) {
+		const int i = bi * 32 + r, j = bj * 32 + tx;
+		if (i < N && j < N && i < j) {
+			const float a = tA[r][tx], b = tB[tx][r];
+			const float scale = sqrtf(fabsf(Q[(size_t)i * ldq + i]) * fabsf(Q[(size_t)j * ldq + j]));
+			if (!(fabsf(a - b) <= tol * scale)) bad++; /* also counts NaN / Inf */
+		}
+	}
+	bad = __reduce_add_sync(0xffffffffu, bad);
+	if (tx == 0 && bad) atomicAdd(mismatch, bad);
+}
+
+__global__ void sym_mean_kernel(float *Q, int ldq, int N, const unsigned *mismatch)
+{
+	__shared__ float tA[32][33], tB[32][33];
+	if (*mismatch) return;
+	const int bi = blockIdx.y, bj = blockIdx.x;
+	if (bi > bj) return;
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	for (int r = ty; r < 32; r += 8) {
+		const int i = bi * 32 + r, j = bj * 32 + tx;
+		tA[r][tx] = (i < N && j < N) ? Q[(size_t)i * ldq + j] : 0.0f;
+		const int i2 = bj * 32 + r, j2 = bi * 32 + tx;
+		tB[r][tx] = (i2 < N && j2 < N) ? Q[(size_t)i2 * ldq + j2] : 0.0f;
+	}
+	__syncthreads();
+	for (int r = ty; r < 32; r += 8) {
+		const int i = bi * 32 + r, j = bj * 32 + tx; /* upper copy (i, j), coalesced along j */
+		if (i < N && j < N && i < j) Q[(size_t)i * ldq + j] = 0.5f * (tA[r][tx] + tB[tx][r]);
+		const int i2 = bj * 32 + r, j2 = bi * 32 + tx; /* lower copy (i2, j2) = mean of (j2, i2) and (i2, j2) */
+		if (i2 < N && j2 < N && j2 < i2) Q[(size_t)i2 * ldq + j2] = 0.5f * (tA[tx][r] + tB[r][tx]);
+	}
+}
+
+cudaError_t pqp_launch_sym_mean(float *Q, int ldq, int N, float tol, unsigned *mismatch, cudaStream_t s)
+{
+	cudaError_t e = cudaMemsetAsync(mismatch, 0, sizeof(unsigned), s);
+	if (e != cudaSuccess) return e;
+	const int nbk = (N + 31) / 32;
+	sym_near_check_kernel<<<dim3(nbk, nbk), dim3(32, 8), 0, s>>>(Q, ldq, N, tol, mismatch);
+	sym_mean_kernel<<<dim3(nbk, nbk), dim3(32, 8), 0, s>>>(Q, ldq, N, mismatch);
+	return cudaGetLastError();
+}
+
 __global__ void sym_build_units_kernel(float *units, const float *Q, int ldq, int N, int nb)
 {
 	const int u = blockIdx.x; /* unit */

@@ -109,6 +109,8 @@ size_t pqp_gemv_sym_units_bytes(int N);
 int pqp_gemv_sym_plan(int N, int grid, size_t smem_budget, int *stages, int *resident);
 int pqp_gemv_sym_tables(int N, int G, int *cta_u0, int *cta_j0, int *strip_c0, int *strip_c1);
 cudaError_t pqp_launch_sym_check(const float *Q, int ldq, int N, unsigned *mismatch, cudaStream_t s);
+/* pqp_setup, FAST order: when every pair (Q_ij, Q_ji) agrees to tol * sqrt(|Q_ii Q_jj|), both become their mean (else Q is left alone) */
+cudaError_t pqp_launch_sym_mean(float *Q, int ldq, int N, float tol, unsigned *mismatch, cudaStream_t s);
 cudaError_t pqp_launch_build_sym_units(float *units, const float *Q, int ldq, int N, cudaStream_t s);
 cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, void *pk0, void *pk1, cudaStream_t s);
 /* strict: one launch per iteration, thread i owns row i and walks k ascending over QT */

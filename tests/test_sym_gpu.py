@@ -236,3 +236,45 @@ def test_sym_units_in_tensor_memory_change_nothing(pqp):
             assert np.array_equal(got["0"][0], got[tm][0]), (N, tm)
             assert got["0"][1] == got[tm][1], (N, tm)
             assert np.array_equal(got["0"][2], got[tm][2]) and got["0"][3] == got[tm][3], (N, tm)
+
+
+def test_setup_gives_a_dense_symmetric_hessian_one_value_per_pair(pqp, oracle32, oracle64):
+    """pqp_setup, FAST order: Qd = Gp Qp_inv Gp' with a DENSE symmetric Qp_inv (the generator's is diagonal) comes out of the GEMM
+    with its two copies of an element differing in the last bits; the setup replaces each pair by its mean when all pairs agree
+    to rounding, so this problem class reaches the upper-triangle loop too.  The result stays within the FAST tolerance of the
+    oracle on the same inputs.  exploit_symmetry = 0 keeps the matrix as computed; an unsymmetric Qp_inv is never touched."""
+    rng = np.random.default_rng(91)
+    M, N, K = 300, 2400, 30
+    A = rng.standard_normal((M, M)).astype(np.float32)
+    Qi = (A.astype(np.float64) @ A.astype(np.float64).T / M + np.eye(M)).astype(np.float32)
+    Qi = np.ascontiguousarray(np.triu(Qi) + np.triu(Qi, 1).T)
+    prob = dict(Qp_inv=Qi, Gp=rng.integers(-1, 2, (N, M)).astype(np.float32), Kp=rng.uniform(0, 100, N).astype(np.float32),
+                Fp=rng.uniform(0, 100, M).astype(np.float32), Mp0=0.0)
+    d = pqp.dims_plain(M, N)
+    with pqp.Solver(d, prob, exploit_symmetry=0) as s:
+        Q0, _, _ = s.dual()
+        Y0, _, _ = s.solve(iters=K)
+        assert not s.last_kernel.startswith("gemv_sym")
+    with pqp.Solver(d, prob) as s:
+        Q1, _, _ = s.dual()
+        Y1, U1, st = s.solve(iters=K, primal=True)
+        assert s.last_kernel.startswith("gemv_sym"), s.last_kernel
+    assert np.array_equal(Q1, Q1.T)
+    assert not np.array_equal(Q0, Q0.T), "the GEMM output was symmetric already: the test instance does not exercise the mean"
+    assert relerr(Q1, Q0) <= 1e-6 and np.array_equal(np.diag(Q1), np.diag(Q0))
+    Qd, Fd, Md, _ = oracle32.convert_to_dual(prob["Qp_inv"], prob["Gp"], prob["Kp"], prob["Fp"], 0.0)
+    y32, _ = oracle32.solve_fixed(Qd, Fd, K)
+    y64, _ = oracle64.solve_fixed(Qd.astype(np.float64), Fd.astype(np.float64), K)
+    check_fast(Y1[0], y32, y64, "dense Qp_inv, upper-triangle loop")
+    check_fast(Y0[0], y32, y64, "dense Qp_inv, full-matrix loop")
+    assert np.array_equal(active_set(Y1[0]), active_set(y32))
+    assert np.array_equal(U1[0], oracle32.recover_u(Y1[0], prob["Fp"], prob["Gp"], prob["Qp_inv"]))
+    # an unsymmetric Qp_inv: Qd is not symmetric even in exact arithmetic -> left exactly as computed
+    bad = dict(prob, Qp_inv=np.ascontiguousarray(Qi + np.triu(np.full((M, M), 0.01, np.float32), 1)))
+    with pqp.Solver(d, bad, exploit_symmetry=0) as s:
+        Qa, _, _ = s.dual()
+    with pqp.Solver(d, bad) as s:
+        Qb, _, _ = s.dual()
+        s.solve(iters=3)
+        assert not s.last_kernel.startswith("gemv_sym")
+    assert np.array_equal(Qa, Qb)
