@@ -389,7 +389,10 @@ def run_ours(args, w, rank, world, local_rank):
                                 "bytes_per_iteration": bytes_iter, "frac_of_8TBs_nominal": achieved / 8000.0,
                                 "algorithmic_bytes": ("strictly upper triangle of the symmetric Qd, 2N(N-1) B, + 16N B of vectors; frac > 1 means "
                                                       "the triangle is served from L2/shared memory, not HBM" if sym else "4*N*ldq + 16N B"),
-                                "full_matrix_equivalent_gbs": (4.0 * N * ldq + 16.0 * N) * args.iters / (k_ms * 1e-3) / 1e9},
+                                "full_matrix_equivalent_gbs": (4.0 * N * ldq + 16.0 * N) * args.iters / (k_ms * 1e-3) / 1e9,
+                                **({"note": "HBM is the roofline the contract names for this path; measured, the upper-triangle loop is "
+                                            "issue/latency-bound at this size (DESIGN.md 8.2: ncu DRAM traffic is about half the algorithmic "
+                                            "bytes, and removing 41% of it did not change the time)"} if sym else {})},
                       gpu_launches=int(launches), clocks=clocks)
         if rank == 0 and not args.no_cpu:
             engine, kind = cpu_engine()
