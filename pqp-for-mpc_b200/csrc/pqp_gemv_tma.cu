@@ -204,18 +204,22 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 		if (lane == 0) {
 			const uint64_t pol_keep = make_policy(g.pol_keep), pol_stream = make_policy(g.pol_stream);
 			/* resident rows: one-time bulk copies, all on full[0]'s first phase */
-			long long idx = 0;
+			/* ring position and phase are stepped, not derived from a row counter: a 64-bit idx % S, idx / S per row and warp was a
+			 * 35-instruction dependent chain in front of every barrier wait (ncu source view: 1/5 of the row loop's instructions) */
+			int ps = 0;
+			uint32_t pph = 0;
 			if (R > 0) {
 				mbar_arrive_expect_tx(&full[0], row_bytes * (uint32_t)R);
 				for (int t = 0; t < R; t++)
 					bulk_g2s(resid + (size_t)t * ldq, a.Q + (size_t)(r0 + t) * ldq, row_bytes, &full[0], pol_stream);
-				idx = 1; /* stage 0 / phase 0 is consumed by the residency handshake */
+				if (++ps == S) { ps = 0; pph ^= 1u; } /* stage 0 / phase 0 is consumed by the residency handshake */
 			}
 			const int T = max(nrows - R, 1), P = min(g.pinned, T);
 			for (int p = 0; p < passes; p++) {
-				for (int t = R; t < nrows; t++, idx++) {
-					const int s = (int)(idx % S);
-					const uint32_t ph = (uint32_t)((idx / S) & 1);
+				for (int t = R; t < nrows; t++) {
+					const int s = ps;
+					const uint32_t ph = pph;
+					if (++ps == S) { ps = 0; pph ^= 1u; }
 					mbar_wait(&empty[s], ph ^ 1u);
 					mbar_arrive_expect_tx(&full[s], row_bytes);
 					bulk_g2s(ring + (size_t)s * ldq, a.Q + (size_t)(r0 + t) * ldq, row_bytes, &full[s],
@@ -228,12 +232,13 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 	}
 
 	/* ================= consumers ================= */
-	long long idx = 0;
+	int cs = 0; /* ring stage and phase of the next streamed row */
+	uint32_t cph = 0;
 	if (R > 0) {
 		mbar_wait(&full[0], 0);
 		__syncwarp();
 		if (lane == 0) mbar_arrive(&empty[0]);
-		idx = 1;
+		if (++cs == S) { cs = 0; cph ^= 1u; }
 	}
 	/* per-row constants of the rows this thread finishes */
 	float th_r = 0.0f, fd_r = 0.0f, kp_tol = a.eac;
@@ -296,10 +301,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 					} else if (tt < R) {
 						src[k] = reinterpret_cast<const float4 *>(resid + (size_t)tt * ldq);
 					} else {
-						sidx[k] = (int)(idx % S);
-						mbar_wait(&full[sidx[k]], (uint32_t)((idx / S) & 1));
-						src[k] = reinterpret_cast<const float4 *>(ring + (size_t)sidx[k] * ldq);
-						idx++;
+						sidx[k] = cs;
+						mbar_wait(&full[cs], cph);
+						src[k] = reinterpret_cast<const float4 *>(ring + (size_t)cs * ldq);
+						if (++cs == S) { cs = 0; cph ^= 1u; }
 					}
 				}
 				float4 q0[YC], q1[YC];
@@ -343,8 +348,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 				if (t < R) {
 					src = reinterpret_cast<const float4 *>(resid + (size_t)t * ldq);
 				} else {
-					s = (int)(idx % S);
-					mbar_wait(&full[s], (uint32_t)((idx / S) & 1));
+					s = cs;
+					mbar_wait(&full[s], cph);
 					src = reinterpret_cast<const float4 *>(ring + (size_t)s * ldq);
 				}
 				float num = 0.0f, den = 0.0f;
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 				if (t >= R) {
 					__syncwarp();
 					if (lane == 0) mbar_arrive(&empty[s]); /* the row is in registers: hand the stage back */
-					idx++;
+					if (++cs == S) { cs = 0; cph ^= 1u; }
 				}
 	#pragma unroll
 				for (int u = 0; u < YC; u++) acc4t(num, den, q[u], yv[u]);
