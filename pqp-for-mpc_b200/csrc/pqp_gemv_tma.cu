@@ -157,11 +157,39 @@ __device__ __forceinline__ void acc4t(float &num, float &den, const float4 q, co
 	num = fmaf(fmaxf(-q.w, 0.0f), y.w, num);
 }
 
+/*
+ * Tensor memory as a second on-chip store for rows (long-row instantiation, YC = 4: N <= 8192).  The loop is HBM-bound and has no
+ * tensor-core work, so the SM's 256 KB of TMEM would sit idle: it holds eight more rows per SM for the whole launch (37 MB over 148
+ * SMs that HBM/L2 do not deliver again on every update).  Warp w reaches lanes 32*(w%4)..+31; a row takes 64 columns: consumer warps
+ * w, w+4, w+8, w+12 share a lane quarter and own columns 16*(w/4)..+15 of the row's slot -- a thread's 16 columns are its four
+ * float4 of the row.  The parked rows are spread evenly through the slab so the TMA ring refills while they are worked on.
+ */
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float4 &q0, float4 &q1, float4 &q2, float4 &q3)
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+		     : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w), "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w), "=f"(q2.x), "=f"(q2.y), "=f"(q2.z),
+		       "=f"(q2.w), "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w)
+		     : "r"(taddr));
+	/* the wait names the registers it makes valid, so that no use of them can be scheduled ahead of it */
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+		     : "+f"(q0.x), "+f"(q0.y), "+f"(q0.z), "+f"(q0.w), "+f"(q1.x), "+f"(q1.y), "+f"(q1.z), "+f"(q1.w), "+f"(q2.x), "+f"(q2.y), "+f"(q2.z),
+		       "+f"(q2.w), "+f"(q3.x), "+f"(q3.y), "+f"(q3.z), "+f"(q3.w));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float4 q0, const float4 q1, const float4 q2, const float4 q3)
+{
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+		     "f"(q0.x), "f"(q0.y), "f"(q0.z), "f"(q0.w), "f"(q1.x), "f"(q1.y), "f"(q1.z), "f"(q1.w), "f"(q2.x), "f"(q2.y), "f"(q2.z), "f"(q2.w),
+		     "f"(q3.x), "f"(q3.y), "f"(q3.z), "f"(q3.w)
+		     : "memory");
+}
+#define TMA_TM_ROWS_MAX 128 /* rows per slab the tensor-memory table covers */
+
 struct TmaGeom {
 	int stages;     /* ring depth S */
 	int resident;   /* R rows per slab kept in shared memory */
 	int pinned;     /* P streamed rows per slab fetched evict_last */
 	int rows_max;
+	int tmem_rows;  /* rows per slab parked in tensor memory (TMU instantiation), 0..8 */
 	int pol_keep, pol_stream; /* 0 normal, 1 evict_first, 2 evict_last, 3 evict_unchanged */
 	uint2 *pk0, *pk1;         /* packet vectors [ldq] (epochs pre-set to 0xFFFFFFFF), NULL = counter barrier + plain y */
 };
@@ -169,9 +197,12 @@ struct TmaGeom {
 /*
  * Shared memory: ring [S][ldq] | resident [R][ldq] | part [2][16][rows_max] | red [16*8] | full[S], empty[S]
  */
-template <int YC>
+template <int YC, bool TMU>
 __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv_args a, const TmaGeom g)
 {
+	static_assert(!TMU || YC == 4, "tensor-memory rows: 16 columns per thread");
+	__shared__ uint32_t tmem_base_s;
+	__shared__ short tm_col[TMU ? TMA_TM_ROWS_MAX : 1]; /* column of row t of the slab in tensor memory, or -1 */
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
 	const int N = a.N, ldq = a.ldq, n4 = ldq / 4;
@@ -197,7 +228,24 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	if (TMU) {
+		const int L = nrows - R, TM = min(g.tmem_rows, L);
+		for (int t = tid; t < nrows; t += TMA_THREADS) {
+			short c = -1;
+			if (t >= R && TM > 0) {
+				const int x = t - R, before = (int)(((long long)x * TM) / L);
+				if ((int)(((long long)(x + 1) * TM) / L) != before) c = (short)(64 * before);
+			}
+			tm_col[t] = c;
+		}
+		if (warp == 0) {
+			asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+		}
+		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	}
 	__syncthreads();
+	if (TMU) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
 	if (warp == PQP_GEMV_WARPS) {
 		/* ================= producer ================= */
@@ -214,9 +262,10 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 					bulk_g2s(resid + (size_t)t * ldq, a.Q + (size_t)(r0 + t) * ldq, row_bytes, &full[0], pol_stream);
 				if (++ps == S) { ps = 0; pph ^= 1u; } /* stage 0 / phase 0 is consumed by the residency handshake */
 			}
-			const int T = max(nrows - R, 1), P = min(g.pinned, T);
+			const int T = max(nrows - R - (TMU ? min(g.tmem_rows, nrows - R) : 0), 1), P = min(g.pinned, T); /* streamed rows per pass */
 			for (int p = 0; p < passes; p++) {
-				for (int t = R; t < nrows; t++) {
+				for (int t = R, k = 0; t < nrows; t++) {
+					if (TMU && tm_col[t] >= 0) continue; /* lives in tensor memory */
 					const int s = ps;
 					const uint32_t ph = pph;
 					if (++ps == S) { ps = 0; pph ^= 1u; }
@@ -224,7 +273,8 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 					mbar_arrive_expect_tx(&full[s], row_bytes);
 					bulk_g2s(ring + (size_t)s * ldq, a.Q + (size_t)(r0 + t) * ldq, row_bytes, &full[s],
 						 /* pinned rows are spread evenly through the slab so L2 hits and HBM misses overlap in time */
-						 (((long long)(t - R + 1) * P) / T != ((long long)(t - R) * P) / T) ? pol_keep : pol_stream);
+						 (((long long)(k + 1) * P) / T != ((long long)k * P) / T) ? pol_keep : pol_stream); /* k: among the streamed rows */
+					k++;
 				}
 			}
 		}
@@ -248,6 +298,24 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 		if (a.Kp) kp_tol = fmaxf(a.erc * a.Kp[r0 + tid], a.eac);
 	}
 	unsigned bar_target = 0;
+	uint32_t tm_mine = 0;
+	if (TMU) {
+		/* park the rows: each consumer thread loads its four float4 of the row and stores them into its lane */
+		tm_mine = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 16);
+		for (int t = R; t < nrows; t++) {
+			const int col = tm_col[t];
+			if (col < 0) continue;
+			const float4 *src = reinterpret_cast<const float4 *>(a.Q + (size_t)(r0 + t) * ldq);
+			float4 q[4];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int c = tid + u * CONSUMERS;
+				q[u] = (c < n4) ? __ldcs(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+			}
+			tmem_st16(tm_mine + (uint32_t)col, q[0], q[1], q[2], q[3]);
+		}
+		asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+	}
 
 	for (int p = 0; p < passes; p++) {
 		const float *y_in = (p & 1) ? a.ybuf1 : a.ybuf0;
@@ -343,30 +411,36 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 			}
 		} else { /* long rows: one row per step (two would need two 32-48 KB stages at once and 2*YC float4 of operands in registers) */
 			for (int t = 0; t < nrows; t++) {
-				const float4 *src;
+				const float4 *src = nullptr;
 				int s = 0;
+				const int col = TMU ? (int)tm_col[t] : -1;
+				const bool ringrow = t >= R && col < 0;
 				if (t < R) {
 					src = reinterpret_cast<const float4 *>(resid + (size_t)t * ldq);
-				} else {
+				} else if (ringrow) {
 					s = cs;
 					mbar_wait(&full[s], cph);
 					src = reinterpret_cast<const float4 *>(ring + (size_t)s * ldq);
 				}
 				float num = 0.0f, den = 0.0f;
 				float4 q[YC];
-	#pragma unroll
-				for (int u = 0; u < YC; u++) {
-					const int c = tid + u * CONSUMERS;
-					q[u] = (c < n4) ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+				if (TMU && col >= 0) {
+					if constexpr (YC == 4) tmem_ld16(tm_mine + (uint32_t)col, q[0], q[1], q[2], q[3]);
+				} else {
+#pragma unroll
+					for (int u = 0; u < YC; u++) {
+						const int c = tid + u * CONSUMERS;
+						q[u] = (c < n4) ? src[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+					}
 				}
-				if (t >= R) {
+				if (ringrow) {
 					__syncwarp();
 					if (lane == 0) mbar_arrive(&empty[s]); /* the row is in registers: hand the stage back */
 					if (++cs == S) { cs = 0; cph ^= 1u; }
 				}
-	#pragma unroll
+#pragma unroll
 				for (int u = 0; u < YC; u++) acc4t(num, den, q[u], yv[u]);
-	#pragma unroll
+#pragma unroll
 				for (int o = 16; o; o >>= 1) {
 					num += __shfl_xor_sync(0xffffffffu, num, o);
 					den += __shfl_xor_sync(0xffffffffu, den, o);
@@ -459,6 +533,11 @@ __global__ void __launch_bounds__(TMA_THREADS, 1) gemv_tma_kernel(const pqp_gemv
 			}
 		}
 	}
+	if (TMU) {
+		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+		consumer_sync();
+		if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base_s) : "memory");
+	}
 }
 
 static size_t tma_smem_bytes(int ldq, const TmaGeom &g)
@@ -512,6 +591,12 @@ cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident
 	g.resident = resident;
 	g.pinned = pinned;
 	g.rows_max = (a->N + a->grid - 1) / a->grid + 1;
+	/* eight rows per slab parked in tensor memory: long-row instantiation only, and only when something is streamed at all */
+	g.tmem_rows = (yc == 4 && g.rows_max <= TMA_TM_ROWS_MAX && resident < g.rows_max) ? 8 : 0;
+	if (getenv("PQP_TMA_TMEM")) {
+		const int v = atoi(getenv("PQP_TMA_TMEM"));
+		if (v >= 0 && v <= 8 && g.tmem_rows) g.tmem_rows = v;
+	}
 	g.pol_keep = 2;
 	g.pol_stream = 1;
 	g.pk0 = reinterpret_cast<uint2 *>(pk0);
@@ -526,10 +611,10 @@ cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident
 	const size_t smem = tma_smem_bytes(a->ldq, g);
 	const void *fn = NULL;
 	switch (yc) {
-	case 1: fn = (const void *)gemv_tma_kernel<1>; break;
-	case 2: fn = (const void *)gemv_tma_kernel<2>; break;
-	case 4: fn = (const void *)gemv_tma_kernel<4>; break;
-	case 8: fn = (const void *)gemv_tma_kernel<8>; break;
+	case 1: fn = (const void *)gemv_tma_kernel<1, false>; break;
+	case 2: fn = (const void *)gemv_tma_kernel<2, false>; break;
+	case 4: fn = g.tmem_rows > 0 ? (const void *)gemv_tma_kernel<4, true> : (const void *)gemv_tma_kernel<4, false>; break;
+	case 8: fn = (const void *)gemv_tma_kernel<8, false>; break;
 	default: return cudaErrorInvalidValue;
 	}
 	cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -278,3 +278,23 @@ def test_setup_gives_a_dense_symmetric_hessian_one_value_per_pair(pqp, oracle32,
         s.solve(iters=3)
         assert not s.last_kernel.startswith("gemv_sym")
     assert np.array_equal(Qa, Qb)
+
+
+def test_full_matrix_loop_rows_in_tensor_memory_change_nothing(pqp):
+    """The full-matrix TMA loop parks eight rows per slab in tensor memory (PQP_TMA_TMEM, long-row instantiation: 4096 < N <= 8192);
+    where a row is kept does not enter the arithmetic: 0, 5 and 8 parked rows give the same bits, also on a ragged size."""
+    import os
+    for N, M, K in ((6100, 1500, 10), (8192, 2048, 5), (4800, 1200, 12)):
+        prob, d = pqp.generate_testproblem(78, M, N)
+        got = {}
+        for tm in ("0", "5", "8"):
+            os.environ["PQP_TMA_TMEM"] = tm
+            try:
+                with pqp.Solver(d, prob, exploit_symmetry=0) as s:
+                    Y, _, st = s.solve(iters=K)
+                    assert s.last_kernel.startswith("gemv_tma"), (N, tm, s.last_kernel)
+                    got[tm] = (Y.copy(), st["Jd"][0], st["gap"][0])
+            finally:
+                os.environ.pop("PQP_TMA_TMEM", None)
+        for tm in ("5", "8"):
+            assert np.array_equal(got["0"][0], got[tm][0]) and got["0"][1:] == got[tm][1:], (N, tm)
