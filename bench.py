@@ -267,7 +267,7 @@ def run_reference(args, w, rank, world):
     out["cpu_baseline"] = {"value": out["value"], "unit": out["unit"], "cores": threads, "kind": kind, "sample": sample}
     out["e2e"] = {"value": out["value"], "unit": out["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     out["gpu_launches"] = 0
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_OUT, flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -519,10 +519,23 @@ def run_ours(args, w, rank, world, local_rank):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": result.pop("ms_per_step"), "higher_is_better": True,
                 "scaling": "strong" if args.workload == "c5" else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic"}
         line.update(result)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
+
+
+_OUT = sys.stdout
+
+
+def own_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle on it and point fd 1 at stderr, so that whatever a library
+    prints there (NCCL's version banner under NCCL_DEBUG=WARN/VERSION, INFO traces) cannot get in front of the line."""
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
 
 def main():
+    own_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
