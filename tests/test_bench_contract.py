@@ -14,6 +14,8 @@ def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
+    # exactly one line on stdout, and nothing else: bench.py owns stdout and sends whatever else writes to fd 1 to stderr
+    assert len(out.stdout.splitlines()) == 1, out.stdout[:500]
     lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
@@ -24,3 +26,13 @@ def test_reference_arm_prints_the_contract_line():
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     e = d["e2e"]
     assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+
+
+def test_stdout_carries_only_the_json_line_even_if_a_library_prints():
+    """A child writing to fd 1 behind Python's back (what NCCL's version banner does) must end up on stderr."""
+    code = ("import os, sys; sys.argv = ['bench.py']; sys.path.insert(0, %r); import bench; bench.own_stdout(); "
+            "os.write(1, b'NCCL version x.y\\n'); print('library noise'); print('{\"ok\": 1}', file=bench._OUT, flush=True)") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout == '{"ok": 1}\n', out.stdout
+    assert "NCCL version x.y" in out.stderr and "library noise" in out.stderr
