@@ -204,6 +204,18 @@ int pqp_solve_batch(pqp_handle *h, const float *X, const float *D, int B, int it
 /* Same loop with the linear term given directly: Fd [B x N] (host or device). */
 int pqp_solve_dual(pqp_handle *h, const float *Fd, int B, int iters, const float *Y0, float *Y, pqp_status *st);
 /*
+ * pqp_solve_dual with the constant of the dual cost given too: Md [B] (host or device; computeMd, PQP_CPU.c:472-479), so that
+ * status.Jd = 1/2 y'Qd y + Fd'y + Md/2 is computeCost's value (PQP_CPU.c:648-666) and the relative gap test of terminate()
+ * (|gap| <= erj*|Jd|, PQP_CPU.c:684) runs against the same scale as the reference's.  Md == NULL is pqp_solve_dual.
+ */
+int pqp_solve_dual_full(pqp_handle *h, const float *Fd, const float *Md, int B, int iters, const float *Y0, float *Y, pqp_status *st);
+/*
+ * Constraint bounds Kp [N] (host or device) for a handle built by pqp_setup_dual, which receives none: the feasibility test of
+ * run-to-tolerance solves then uses compare()'s per-row tolerance max(erc*Kp_i, eac) (PQP_CPU.c:334-343) instead of eac alone.
+ * NULL removes them again.  (pqp_setup takes Kp from the problem.)
+ */
+int pqp_set_constraint_bounds(pqp_handle *h, const float *Kp);
+/*
  * U_b = -Qp_inv*(Gp'*Y_b + Fp_b), computeUfromY PQP_CPU.c:352-360, with Fp_b the vectors the
  * last pqp_solve_batch on this handle formed (pass Fp != NULL [B x M] to override, e.g. after
  * pqp_solve_dual).  Y: host or device, U [B x M]: host or device.
@@ -241,6 +253,20 @@ int pqp_matmul(float *out, const float *A, int tA, const float *B, int tB, int a
 int pqp_update_y2(float *Y_next, const float *Y, const float *Qdp_theta, const float *Qdn_theta, const float *Fdp, const float *Fdn, int N,
 		  int device);
 
+/*
+ * The reference's small free functions on the device, in the reference's own summation order (bit-identical to PQP_CPU.c), for
+ * callers that hold host arrays and no handle (libpqp_compat.so): all pointers host or device, device < 0 = current.
+ *   pqp_compute_fp        Fp = Fp1*D + Fp2*x - Fp3                       computeFp      PQP_CPU.c:373-382
+ *   pqp_compute_cost      J  = 1/2 Z'QZ + F'Z + Mc/2  (Mc NULL: 0)        computeCost    PQP_CPU.c:648-666
+ *   pqp_compute_md        Md = Fp'Qp_inv Fp - Mp      (Mp NULL: 0)        computeMd      PQP_CPU.c:472-479
+ *   pqp_compute_u_from_y  U_b = -Qp_inv (Gp'Y_b + Fp_b), b < B            computeUfromY  PQP_CPU.c:352-360
+ */
+int pqp_compute_fp(float *Fp, const float *Fp1, const float *Fp2, const float *Fp3, const float *D, const float *x, int M, int nDisH, int nState,
+		   int device);
+int pqp_compute_cost(float *J, const float *Z, const float *Q, const float *F, const float *Mc, int N, int device);
+int pqp_compute_md(float *Md, const float *Fp, const float *Qp_inv, const float *Mp, int M, int device);
+int pqp_compute_u_from_y(float *U, const float *Y, const float *Fp, const float *Gp, const float *Qp_inv, int N, int M, int B, int device);
+
 /* ---- introspection (tests, benches) ----------------------------------------------------- */
 /* copies out what setup built; any pointer may be NULL.  Qd [N x N], theta [N], GQ [N x M] (host buffers) */
 int pqp_get_dual(pqp_handle *h, float *Qd, float *theta, float *GQ);
@@ -250,6 +276,9 @@ int pqp_get_linear_terms(pqp_handle *h, int B, float *Fd, float *Fp);
 void *pqp_get_stream(pqp_handle *h);
 /* device time of the iteration kernel(s) of the last solve, in ms (CUDA events on the handle's stream) */
 float pqp_last_solve_ms(pqp_handle *h);
+/* device time, in ms, of the two GEMMs of convertToDual (GQ = Gp*Qp_inv, Qd = GQ*Gp'; PQP_CPU.c:492, :442) inside pqp_setup
+ * (2*N*M*M + 2*N*N*M flop); 0 for a handle built by pqp_setup_dual */
+float pqp_setup_gemm_ms(pqp_handle *h);
 /* how many of this library's kernels the handle has launched so far */
 long long pqp_launch_count(pqp_handle *h);
 /* name of the iteration kernel the last solve used ("gemv_tma_stream", "gemv_strict", "batched_imma", "batched_simt", ...) */

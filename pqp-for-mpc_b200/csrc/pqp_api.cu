@@ -18,6 +18,34 @@
 
 static thread_local char g_cuda_err[512] = "";
 
+/* ---- the handle's snapshot of the PQP_* environment (pqp_internal.h) ---------------------------------------------------------- */
+extern char **environ;
+struct pqp_env_snapshot {
+	int n;
+	char *kv[96]; /* "NAME=value" copies */
+};
+static thread_local const pqp_env_snapshot *g_env = NULL;
+
+static void env_snapshot_take(pqp_env_snapshot *e)
+{
+	e->n = 0;
+	for (char **p = environ; p && *p && e->n < (int)(sizeof e->kv / sizeof e->kv[0]); p++)
+		if (!strncmp(*p, "PQP_", 4)) e->kv[e->n++] = strdup(*p);
+}
+static void env_snapshot_free(pqp_env_snapshot *e)
+{
+	for (int i = 0; i < e->n; i++) free(e->kv[i]);
+	e->n = 0;
+}
+const char *pqp_env(const char *name)
+{
+	if (!g_env) return getenv(name);
+	const size_t len = strlen(name);
+	for (int i = 0; i < g_env->n; i++)
+		if (g_env->kv[i] && !strncmp(g_env->kv[i], name, len) && g_env->kv[i][len] == '=') return g_env->kv[i] + len + 1;
+	return NULL;
+}
+
 #define CK(call)                                                                                          \
 	do {                                                                                              \
 		cudaError_t e__ = (call);                                                                 \
@@ -65,6 +93,17 @@ struct pqp_handle {
 	int l2_window_set;
 	long long launches;
 	const char *last_kernel;
+	pqp_env_snapshot env; /* PQP_* knobs as they were when the handle was created */
+	float setup_gemm_ms;   /* device time of the two dual-construction GEMMs (GQ, Qd) in pqp_setup */
+	size_t l2_limit_saved; /* cudaLimitPersistingL2CacheSize before this handle changed it */
+	int l2_limit_changed;
+};
+
+/* every public entry point that takes a handle: its knobs are the calling thread's current ones until the next entry */
+struct env_scope {
+	const pqp_env_snapshot *prev;
+	explicit env_scope(const pqp_handle *h) : prev(g_env) { g_env = h ? &h->env : NULL; }
+	~env_scope() { g_env = prev; }
 };
 
 const char *pqp_last_cuda_error(void) { return g_cuda_err; }
@@ -150,6 +189,22 @@ static int upload(pqp_handle *h, float **dst, const float *src, size_t n)
 	return PQP_OK;
 }
 
+/* the persisting-L2 carve-out is device-global state: remember what it was the first time this handle changes it, so that
+ * pqp_destroy can put it back */
+static cudaError_t set_l2_carveout(pqp_handle *h, size_t bytes)
+{
+	if (!h->l2_limit_changed) {
+		size_t cur = 0;
+		if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess) {
+			h->l2_limit_saved = cur;
+			h->l2_limit_changed = 1;
+		} else {
+			cudaGetLastError();
+		}
+	}
+	return cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+}
+
 static int open_device(pqp_handle *h, const pqp_opts *opts)
 {
 	int n = 0;
@@ -169,14 +224,14 @@ static int open_device(pqp_handle *h, const pqp_opts *opts)
 	int optin = 0;
 	CK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
 	h->smem_optin = (size_t)optin;
-	if (getenv("PQP_L2_CARVEOUT_MB")) {
+	if (pqp_env("PQP_L2_CARVEOUT_MB")) {
 		/* experiment knob: size of the persisting-L2 carve-out (evict_last lines live there) */
 		int maxp = 0;
 		cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, dev);
-		size_t want = (size_t)atoi(getenv("PQP_L2_CARVEOUT_MB")) << 20;
+		size_t want = (size_t)atoi(pqp_env("PQP_L2_CARVEOUT_MB")) << 20;
 		if (want > (size_t)maxp) want = (size_t)maxp;
-		CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
-		if (getenv("PQP_VERBOSE")) fprintf(stderr, "pqp: persisting L2 max %d MB, set %zu MB\n", maxp >> 20, want >> 20);
+		CK(set_l2_carveout(h, want));
+		if (pqp_env("PQP_VERBOSE")) fprintf(stderr, "pqp: persisting L2 max %d MB, set %zu MB\n", maxp >> 20, want >> 20);
 	}
 	CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&h->ev0));
@@ -242,8 +297,8 @@ static int finish_setup(pqp_handle *h)
 	int grid = h->num_sms;
 	if (grid > (N + 3) / 4) grid = (N + 3) / 4;
 	if (grid < 1) grid = 1;
-	if (getenv("PQP_GEMV_GRID")) {
-		int v = atoi(getenv("PQP_GEMV_GRID"));
+	if (pqp_env("PQP_GEMV_GRID")) {
+		int v = atoi(pqp_env("PQP_GEMV_GRID"));
 		if (v >= 1 && v <= h->num_sms && v <= N) grid = v;
 	}
 	h->gemv_grid = grid;
@@ -260,7 +315,7 @@ static int finish_setup(pqp_handle *h)
 		h->gemv_grid = 0; /* y does not fit in shared memory: persistent kernel unavailable */
 		res = 0;
 	}
-	const char *env = getenv("PQP_GEMV_RESIDENT");
+	const char *env = pqp_env("PQP_GEMV_RESIDENT");
 	if (env) {
 		int v = atoi(env);
 		if (v >= 0 && v < res) res = v;
@@ -271,12 +326,12 @@ static int finish_setup(pqp_handle *h)
 
 	/* register-resident kernel for small N */
 	h->small_ok = 0;
-	if (h->gemv_grid > 0 && !(getenv("PQP_GEMV_SMALL") && atoi(getenv("PQP_GEMV_SMALL")) == 0)) {
+	if (h->gemv_grid > 0 && !(pqp_env("PQP_GEMV_SMALL") && atoi(pqp_env("PQP_GEMV_SMALL")) == 0)) {
 		/* as FEW CTAs as the 16-rows-per-CTA layout allows: the y exchange costs ~1 us with 32-64 participants and
 		 * ~3.4 us with 148 (measured, tools/gemv_sweep.py N=1024), and the arithmetic is negligible either way */
 		int sg = (N + 15) / 16;
 		if (sg > h->num_sms) sg = h->num_sms;
-		if (getenv("PQP_GEMV_GRID")) sg = h->gemv_grid;
+		if (pqp_env("PQP_GEMV_GRID")) sg = h->gemv_grid;
 		h->small_grid = sg;
 		h->small_ok = pqp_gemv_small_plan(N, ldq, sg, &h->small_wpr, &h->small_cpt);
 	}
@@ -286,17 +341,17 @@ static int finish_setup(pqp_handle *h)
 	if (h->gemv_grid > 0) {
 		h->tma_ok = pqp_gemv_tma_plan(N, ldq, h->gemv_grid, budget, &h->tma_stages, &h->tma_resident, &h->tma_yc);
 		const char *e;
-		if ((e = getenv("PQP_GEMV_TMA")) && atoi(e) == 0) h->tma_ok = 0;
+		if ((e = pqp_env("PQP_GEMV_TMA")) && atoi(e) == 0) h->tma_ok = 0;
 		if (h->tma_ok) {
 			const int total = h->tma_stages + h->tma_resident;
-			if ((e = getenv("PQP_TMA_STAGES"))) {
+			if ((e = pqp_env("PQP_TMA_STAGES"))) {
 				int v = atoi(e);
 				if (v >= 2 && v <= total && h->tma_resident < rows_max) {
 					h->tma_stages = v;
 					h->tma_resident = total - v;
 				}
 			}
-			if ((e = getenv("PQP_TMA_RESIDENT"))) {
+			if ((e = pqp_env("PQP_TMA_RESIDENT"))) {
 				int v = atoi(e);
 				if (v >= 0 && v < h->tma_resident) h->tma_resident = v;
 			}
@@ -311,10 +366,10 @@ static int finish_setup(pqp_handle *h)
 				cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, h->device);
 				size_t want = (size_t)64 << 20;
 				if (want > (size_t)maxp) want = (size_t)maxp;
-				if (!getenv("PQP_L2_CARVEOUT_MB")) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+				if (!pqp_env("PQP_L2_CARVEOUT_MB")) set_l2_carveout(h, want);
 			}
-			if ((e = getenv("PQP_L2_PIN_ROWS"))) h->tma_pinned = atoi(e) > 0 ? atoi(e) : 0;
-			if (getenv("PQP_VERBOSE"))
+			if ((e = pqp_env("PQP_L2_PIN_ROWS"))) h->tma_pinned = atoi(e) > 0 ? atoi(e) : 0;
+			if (pqp_env("PQP_VERBOSE"))
 				fprintf(stderr, "pqp: gemv_tma N=%d grid=%d stages=%d resident=%d pinned=%d yc=%d\n", N, h->gemv_grid,
 					h->tma_stages, h->tma_resident, h->tma_pinned, h->tma_yc);
 		}
@@ -336,11 +391,11 @@ static int l2_persist_window(pqp_handle *h, int enable)
 	if (enable) {
 		const size_t qbytes = (size_t)h->d.N * h->ldq * sizeof(float);
 		size_t persist = (size_t)prop.persistingL2CacheMaxSize;
-		const char *env = getenv("PQP_L2_PERSIST_MB");
+		const char *env = pqp_env("PQP_L2_PERSIST_MB");
 		if (env) persist = (size_t)atoi(env) << 20;
 		if (persist == 0) return PQP_OK;
 		if (persist > (size_t)prop.persistingL2CacheMaxSize) persist = (size_t)prop.persistingL2CacheMaxSize;
-		CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+		CK(set_l2_carveout(h, persist));
 		size_t win = qbytes < (size_t)prop.accessPolicyMaxWindowSize ? qbytes : (size_t)prop.accessPolicyMaxWindowSize;
 		v.accessPolicyWindow.base_ptr = (void *)h->Q;
 		v.accessPolicyWindow.num_bytes = win;
@@ -375,6 +430,8 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 	h->d = *dims;
 	h->o = o;
 	h->last_kernel = "none";
+	env_snapshot_take(&h->env);
+	env_scope scope(h);
 	int rc = open_device(h, &o);
 	if (rc) { pqp_destroy(h); return rc; }
 
@@ -402,6 +459,7 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 	if ((rc = dalloc(&h->GQ, (size_t)N * M)) || (rc = dalloc(&h->Q, (size_t)N * h->ldq))) { pqp_destroy(h); return rc; }
 	cudaError_t e = cudaMemsetAsync(h->Q, 0, (size_t)N * h->ldq * sizeof(float), h->stream);
 	/* GQ = Gp*Qp_inv (PQP_CPU.c:492), Qd = GQ*Gp' (PQP_CPU.c:442) */
+	if (e == cudaSuccess) e = cudaEventRecord(h->ev0, h->stream);
 	if (e == cudaSuccess) {
 		if (strict) {
 			e = pqp_launch_matmul_strict(h->GQ, M, h->Gp, M, h->Qp_inv, M, 0, N, M, M, h->stream);
@@ -421,6 +479,9 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 			if (e == cudaSuccess) e = pqp_launch_matmul_simt(h->Q, h->ldq, h->GQ, M, h->Gp, M, 1, N, M, N, h->stream);
 		}
 		h->launches += 2;
+		if (e == cudaSuccess) e = cudaEventRecord(h->ev1, h->stream);
+		if (e == cudaSuccess) e = cudaEventSynchronize(h->ev1);
+		if (e == cudaSuccess) e = cudaEventElapsedTime(&h->setup_gemm_ms, h->ev0, h->ev1);
 	}
 	if (e != cudaSuccess) {
 		snprintf(g_cuda_err, sizeof g_cuda_err, "setup GEMMs -> %s", cudaGetErrorString(e));
@@ -443,7 +504,7 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 			pqp_destroy(h);
 			return PQP_ERR_CUDA;
 		}
-		if (getenv("PQP_VERBOSE")) fprintf(stderr, "pqp: setup: %u pairs of Qd differ by more than rounding%s\n", bad, bad ? " (left as computed)" : " (both copies set to their mean)");
+		if (pqp_env("PQP_VERBOSE")) fprintf(stderr, "pqp: setup: %u pairs of Qd differ by more than rounding%s\n", bad, bad ? " (left as computed)" : " (both copies set to their mean)");
 	}
 	if ((rc = finish_setup(h))) { pqp_destroy(h); return rc; }
 	*out = h;
@@ -465,6 +526,8 @@ int pqp_setup_dual(pqp_handle **out, int N, const float *Qd, int M, const float 
 	h->d.M = (Gp && Qp_inv && M > 0) ? M : 0;
 	h->o = o;
 	h->last_kernel = "none";
+	env_snapshot_take(&h->env);
+	env_scope scope(h);
 	int rc = open_device(h, &o);
 	if (rc) { pqp_destroy(h); return rc; }
 	h->ldq = pqp_round_up(N, 32);
@@ -497,6 +560,7 @@ void pqp_destroy(pqp_handle *h)
 		cudaSetDevice(h->device);
 		cudaStreamSynchronize(h->stream);
 		if (h->l2_window_set) l2_persist_window(h, 0);
+		if (h->l2_limit_changed) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_limit_saved);
 	}
 	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
 			 h->Kx, h->Kd, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
@@ -508,6 +572,7 @@ void pqp_destroy(pqp_handle *h)
 	if (h->ev1) cudaEventDestroy(h->ev1);
 	if (h->stream) cudaStreamDestroy(h->stream);
 	cudaGetLastError();
+	env_snapshot_free(&h->env);
 	free(h);
 }
 
@@ -523,7 +588,7 @@ static int ensure_sym(pqp_handle *h)
 	h->sym_state = -1;
 	const int N = h->d.N, G = h->gemv_grid;
 	const char *e;
-	if ((e = getenv("PQP_GEMV_SYM")) && atoi(e) == 0) return PQP_OK;
+	if ((e = pqp_env("PQP_GEMV_SYM")) && atoi(e) == 0) return PQP_OK;
 	if (!h->o.exploit_symmetry || h->o.order == PQP_ORDER_STRICT || G <= 0 || h->small_ok) return PQP_OK;
 	const size_t budget = h->smem_optin > 1024 ? h->smem_optin - 1024 : 0;
 	pqp_sym_plan pl;
@@ -532,12 +597,13 @@ static int ensure_sym(pqp_handle *h)
 	unsigned *bad_dev = NULL, bad = 1;
 	int rc;
 	if ((rc = dalloc(&bad_dev, 1))) return rc;
-	CK(pqp_launch_sym_check(h->Q, h->ldq, N, bad_dev, h->stream));
+	cudaError_t ce0 = pqp_launch_sym_check(h->Q, h->ldq, N, bad_dev, h->stream);
 	h->launches++;
-	CK(cudaMemcpyAsync(&bad, bad_dev, sizeof bad, cudaMemcpyDeviceToHost, h->stream));
-	CK(cudaStreamSynchronize(h->stream));
+	if (ce0 == cudaSuccess) ce0 = cudaMemcpyAsync(&bad, bad_dev, sizeof bad, cudaMemcpyDeviceToHost, h->stream);
+	if (ce0 == cudaSuccess) ce0 = cudaStreamSynchronize(h->stream);
 	cudaFree(bad_dev);
-	if (getenv("PQP_VERBOSE")) fprintf(stderr, "pqp: symmetry test of Qd: %u unequal pairs\n", bad);
+	CK(ce0);
+	if (pqp_env("PQP_VERBOSE")) fprintf(stderr, "pqp: symmetry test of Qd: %u unequal pairs\n", bad);
 	if (bad) return PQP_OK;
 
 	pqp_gemv_sym_counts(N, &pl.nb, &pl.U);
@@ -546,7 +612,7 @@ static int ensure_sym(pqp_handle *h)
 	int *cta_u0 = tab, *cta_j0 = tab + G + 1, *strip_c0 = cta_j0 + G, *strip_c1 = strip_c0 + pl.nb;
 	pl.maxseg = pqp_gemv_sym_tables(N, G, cta_u0, cta_j0, strip_c0, strip_c1);
 	const int umax = (pl.U + G - 1) / G;
-	if ((e = getenv("PQP_SYM_RESIDENT"))) {
+	if ((e = pqp_env("PQP_SYM_RESIDENT"))) {
 		int v = atoi(e);
 		if (v >= 0 && v < pl.resident) pl.resident = v;
 	}
@@ -560,7 +626,7 @@ static int ensure_sym(pqp_handle *h)
 	 * parked) 14.9 -> 13.0 -- and not at N=8192 (8 of 28: 19.3 -> 19.4-19.7): used while at least half of the units outside shared
 	 * memory fit */
 	pl.tmem = (umax - pl.resident <= 16) ? 8 : 0;
-	if ((e = getenv("PQP_SYM_TMEM"))) {
+	if ((e = pqp_env("PQP_SYM_TMEM"))) {
 		int v = atoi(e);
 		if (v >= 0 && v <= 8) pl.tmem = v;
 	}
@@ -568,11 +634,11 @@ static int ensure_sym(pqp_handle *h)
 	const int streamed = umax - pl.resident - pl.tmem > 0 ? umax - pl.resident - pl.tmem : 0;
 	const double unit_bytes = 64.0 * 128.0 * 4.0;
 	double frac = 0.5; /* measured at N=8192 (29 units per CTA): 10-16 units per CTA evict_last is a plateau (19.6 us/update); 0: 25.2, 8: 20.5, 18: 20.1, 28: 25.9 */
-	if ((e = getenv("PQP_SYM_PIN_FRAC"))) frac = atof(e);
+	if ((e = pqp_env("PQP_SYM_PIN_FRAC"))) frac = atof(e);
 	pl.pinned = streamed;
 	if ((double)streamed * G * unit_bytes > 0.8 * (double)l2_bytes) pl.pinned = (int)(frac * (double)l2_bytes / ((double)G * unit_bytes));
 	if (!h->o.l2_persist) pl.pinned = 0;
-	if ((e = getenv("PQP_SYM_PIN"))) pl.pinned = atoi(e) > 0 ? atoi(e) : 0;
+	if ((e = pqp_env("PQP_SYM_PIN"))) pl.pinned = atoi(e) > 0 ? atoi(e) : 0;
 
 	const size_t nT = (size_t)pl.nb * (pl.nb + 1) / 2;
 	pl.rowpart_bytes = 2 * nT * 128 * 16;
@@ -600,7 +666,7 @@ static int ensure_sym(pqp_handle *h)
 	h->sym = pl; /* owned by the handle from here on (freed in pqp_destroy) */
 	CK(ce);
 	h->launches++;
-	if (getenv("PQP_VERBOSE"))
+	if (pqp_env("PQP_VERBOSE"))
 		fprintf(stderr, "pqp: gemv_sym N=%d grid=%d units=%d (%d per CTA) stages=%d resident=%d tmem=%d pinned=%d maxseg=%d\n", N, G, pl.U, umax,
 			pl.stages, pl.resident, pl.tmem, pl.pinned, pl.maxseg);
 	h->sym_state = 1;
@@ -638,7 +704,7 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 			h->launches += iters;
 			done = iters;
 			if (want_status) {
-				CK(pqp_launch_status(st_dev, h->Q, ldq, N, bufs[done & 1], ldq, Fd, Md, h->Kp, h->o.erc, h->o.eac, 1, done, h->stream));
+				CK(pqp_launch_status(st_dev, h->Q, ldq, N, bufs[done & 1], ldq, Fd, Md, h->Kp, h->o.erc, h->o.eac, 1, done, NULL, h->stream));
 				h->launches++;
 			}
 		} else {
@@ -646,12 +712,14 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 			pqp_status hs;
 			memset(&hs, 0, sizeof hs);
 			for (;;) {
-				CK(pqp_launch_status(st_dev, h->Q, ldq, N, bufs[done & 1], ldq, Fd, Md, h->Kp, h->o.erc, h->o.eac, 1, done, h->stream));
+				float viol = INFINITY; /* max_i(-g_i - max(erc*Kp_i, eac)): the per-row tolerance of compare(), PQP_CPU.c:338 */
+				CK(pqp_launch_status(st_dev, h->Q, ldq, N, bufs[done & 1], ldq, Fd, Md, h->Kp, h->o.erc, h->o.eac, 1, done, h->partials, h->stream));
 				h->launches++;
 				CK(cudaMemcpyAsync(&hs, st_dev, sizeof hs, cudaMemcpyDeviceToHost, h->stream));
+				CK(cudaMemcpyAsync(&viol, h->partials, sizeof viol, cudaMemcpyDeviceToHost, h->stream));
 				CK(cudaStreamSynchronize(h->stream));
-				const float tolc = h->o.eac; /* slack test: -g <= max(erc*Kp, eac) ~ eac-level here */
-				const int conv = hs.min_slack >= -tolc && fabsf(hs.gap) <= h->o.eaj && fabsf(hs.gap) <= h->o.erj * fabsf(hs.Jd);
+				/* the same three conditions the fused kernels test (gemv_cta/small/sym, batched_imma) */
+				const int conv = viol <= 0.0f && fabsf(hs.gap) <= h->o.eaj && fabsf(hs.gap) <= h->o.erj * fabsf(hs.Jd);
 				if (conv || done >= h->o.max_iters) {
 					hs.converged = conv;
 					CK(cudaMemcpyAsync(st_dev, &hs, sizeof hs, cudaMemcpyHostToDevice, h->stream));
@@ -666,7 +734,7 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		return PQP_OK;
 	}
 
-	if (pqp_gemv_cta_supported(N) && !(getenv("PQP_GEMV_CTA") && atoi(getenv("PQP_GEMV_CTA")) == 0)) {
+	if (pqp_gemv_cta_supported(N) && !(pqp_env("PQP_GEMV_CTA") && atoi(pqp_env("PQP_GEMV_CTA")) == 0)) {
 		/* a problem that fits one thread block: no exchange through L2 at all */
 		h->last_kernel = iters > 0 ? "gemv_cta" : "gemv_cta_tol";
 		CK(pqp_launch_gemv_cta(&a, h->stream));
@@ -675,7 +743,7 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		return PQP_OK;
 	}
 	if (h->gemv_grid <= 0) return PQP_ERR_UNSUPPORTED;
-	if (h->small_ok && !(iters <= 0 && getenv("PQP_GEMV_SMALL_TOL") && atoi(getenv("PQP_GEMV_SMALL_TOL")) == 0)) {
+	if (h->small_ok && !(iters <= 0 && pqp_env("PQP_GEMV_SMALL_TOL") && atoi(pqp_env("PQP_GEMV_SMALL_TOL")) == 0)) {
 		/* fixed count, or run to tolerance with the stop test evaluated in the kernel every check_every updates */
 		h->last_kernel = iters > 0 ? "gemv_small_registers" : "gemv_small_registers_tol";
 		a.grid = h->small_grid;
@@ -684,7 +752,7 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		*y_res = h->ybuf1;
 		return PQP_OK;
 	}
-	if (!(iters <= 0 && getenv("PQP_GEMV_SYM_TOL") && atoi(getenv("PQP_GEMV_SYM_TOL")) == 0)) {
+	if (!(iters <= 0 && pqp_env("PQP_GEMV_SYM_TOL") && atoi(pqp_env("PQP_GEMV_SYM_TOL")) == 0)) {
 		/* fixed count, or run to tolerance with the stop test evaluated by the owners every check_every updates */
 		int rc = ensure_sym(h);
 		if (rc) return rc;
@@ -699,7 +767,7 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 	}
 	if (iters > 0 && h->tma_ok) {
 		h->last_kernel = h->tma_resident >= (N + h->gemv_grid - 1) / h->gemv_grid + 1 ? "gemv_tma_resident" : "gemv_tma_stream";
-		const int ll = !(getenv("PQP_GEMV_LL") && atoi(getenv("PQP_GEMV_LL")) == 0);
+		const int ll = !(pqp_env("PQP_GEMV_LL") && atoi(pqp_env("PQP_GEMV_LL")) == 0);
 		CK(pqp_launch_gemv_tma(&a, h->tma_stages, h->tma_resident, h->tma_pinned, h->tma_yc, ll ? h->pk0 : NULL, ll ? h->pk1 : NULL,
 				       h->stream));
 		h->launches++;
@@ -731,10 +799,10 @@ static int batched_engine(const pqp_handle *h)
 	 * PQP_CPU.c's own fp32 arithmetic.  2 -> the 3xTF32 kernel: its fp32 accumulator truncates on every step, which leaves the loop
 	 * 5-100x above the fp32 noise floor after 1000 updates, so it is opt-in only.  PQP_BATCHED=simt|imma|umma overrides.
 	 */
-	const char *e = getenv("PQP_BATCHED");
+	const char *e = pqp_env("PQP_BATCHED");
 	int want = h->o.use_tensor_cores <= 0 ? BATCH_SIMT : (h->o.use_tensor_cores >= 2 ? BATCH_UMMA : BATCH_IMMA);
 	if (e) want = !strcmp(e, "simt") ? BATCH_SIMT : (!strcmp(e, "umma") ? BATCH_UMMA : (!strcmp(e, "imma") ? BATCH_IMMA : want));
-	if (getenv("PQP_BATCHED_UMMA")) want = atoi(getenv("PQP_BATCHED_UMMA")) ? BATCH_UMMA : BATCH_SIMT; /* older knob */
+	if (pqp_env("PQP_BATCHED_UMMA")) want = atoi(pqp_env("PQP_BATCHED_UMMA")) ? BATCH_UMMA : BATCH_SIMT; /* older knob */
 	if (want == BATCH_IMMA && !pqp_batched_imma_supported(h->d.N)) want = BATCH_SIMT;
 	if (want == BATCH_UMMA && !pqp_batched_umma_supported(h->d.N)) want = BATCH_SIMT;
 	return want;
@@ -805,14 +873,14 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			/* problems per CTA: 32 (measured faster than 64 at every batch size: 195k vs 103k solves/s at B=4096, 225k vs 165k
 			 * at B=32768; the 64-problem tile is kept as an experiment knob) */
 			int nb = 32;
-			if (getenv("PQP_IMMA_NB")) nb = atoi(getenv("PQP_IMMA_NB")) == 64 ? 64 : 32;
+			if (pqp_env("PQP_IMMA_NB")) nb = atoi(pqp_env("PQP_IMMA_NB")) == 64 ? 64 : 32;
 			int cluster = 1;
-			if (getenv("PQP_IMMA_CLUSTER")) cluster = atoi(getenv("PQP_IMMA_CLUSTER"));
+			if (pqp_env("PQP_IMMA_CLUSTER")) cluster = atoi(pqp_env("PQP_IMMA_CLUSTER"));
 			if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) cluster = 1;
 			/* fixed count, more than one 32-problem tile, at least two M tiles: the CTA-pair kernel (64 problems per pair, rows of Q
 			 * split over the two SMs) moves half the operand bytes per problem through shared memory */
 			const int pair = iters > 0 && B > 32 && pqp_batched_imma_pair_supported(N) &&
-					 (getenv("PQP_IMMA_PAIR") ? atoi(getenv("PQP_IMMA_PAIR")) != 0 : 1);
+					 (pqp_env("PQP_IMMA_PAIR") ? atoi(pqp_env("PQP_IMMA_PAIR")) != 0 : 1);
 			if (pair) {
 				CK(pqp_launch_batched_imma_pair(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, h->smem_optin, h->stream));
 				h->last_kernel = "batched_imma_pair";
@@ -826,7 +894,7 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			}
 		} else if (engine == BATCH_UMMA) {
 			int cluster = 4;
-			if (getenv("PQP_UMMA_CLUSTER")) cluster = atoi(getenv("PQP_UMMA_CLUSTER"));
+			if (pqp_env("PQP_UMMA_CLUSTER")) cluster = atoi(pqp_env("PQP_UMMA_CLUSTER"));
 			if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8) cluster = 1;
 			CK(pqp_launch_batched_umma(h->umma_tiles, N, B, h->Fd, h->Y, iters, cluster, h->stream));
 			h->last_kernel = "batched_umma";
@@ -838,12 +906,12 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 		h->ev_valid = 1;
 		h->launches++;
 		if (want_status && iters > 0) { /* in tolerance mode the kernel wrote the status of every problem itself */
-			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, Md, h->Kp, h->o.erc, h->o.eac, B, iters, h->stream));
+			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, Md, h->Kp, h->o.erc, h->o.eac, B, iters, NULL, h->stream));
 			h->launches++;
 		}
 	} else {
 		/* single-problem kernel, one problem after the other */
-		if (h->o.l2_persist && getenv("PQP_L2_WINDOW") && !strict && !h->l2_window_set) {
+		if (h->o.l2_persist && pqp_env("PQP_L2_WINDOW") && !strict && !h->l2_window_set) {
 			int rc = l2_persist_window(h, 1);
 			if (rc) return rc;
 		}
@@ -897,6 +965,7 @@ int pqp_solve_batch(pqp_handle *h, const float *X, const float *D, int B, int it
 		    pqp_status *st)
 {
 	if (!h || B <= 0) return PQP_ERR_INVALID;
+	env_scope scope(h);
 	CK(cudaSetDevice(h->device));
 	int rc = ensure_capacity(h, B);
 	if (rc) return rc;
@@ -906,19 +975,44 @@ int pqp_solve_batch(pqp_handle *h, const float *X, const float *D, int B, int it
 	return PQP_OK;
 }
 
-int pqp_solve_dual(pqp_handle *h, const float *Fd, int B, int iters, const float *Y0, float *Y, pqp_status *st)
+int pqp_solve_dual_full(pqp_handle *h, const float *Fd, const float *Md, int B, int iters, const float *Y0, float *Y, pqp_status *st)
 {
 	if (!h || B <= 0 || !Fd) return PQP_ERR_INVALID;
+	env_scope scope(h);
 	CK(cudaSetDevice(h->device));
 	int rc = ensure_capacity(h, B);
 	if (rc) return rc;
 	CK(cudaMemcpyAsync(h->Fd, Fd, (size_t)B * h->d.N * sizeof(float), cudaMemcpyDefault, h->stream));
+	if (Md) CK(cudaMemcpyAsync(h->Md, Md, (size_t)B * sizeof(float), cudaMemcpyDefault, h->stream));
 	h->fp_B = 0;
 	const int saved = h->have_fp_model;
-	h->have_fp_model = 0; /* no Md without Fp: Jd is reported without the constant */
+	h->have_fp_model = Md != NULL; /* without Md, Jd is reported (and tested) without the constant Md/2 */
 	rc = run_loop(h, B, iters, Y0, Y, st);
 	h->have_fp_model = saved;
 	if (rc) return rc;
+	CK(cudaStreamSynchronize(h->stream));
+	return PQP_OK;
+}
+
+int pqp_solve_dual(pqp_handle *h, const float *Fd, int B, int iters, const float *Y0, float *Y, pqp_status *st)
+{
+	return pqp_solve_dual_full(h, Fd, NULL, B, iters, Y0, Y, st);
+}
+
+int pqp_set_constraint_bounds(pqp_handle *h, const float *Kp)
+{
+	if (!h) return PQP_ERR_INVALID;
+	CK(cudaSetDevice(h->device));
+	if (!Kp) {
+		if (h->Kp) cudaFree(h->Kp);
+		h->Kp = NULL;
+		return PQP_OK;
+	}
+	if (!h->Kp) {
+		int rc = dalloc(&h->Kp, (size_t)h->d.N);
+		if (rc) return rc;
+	}
+	CK(cudaMemcpyAsync(h->Kp, Kp, (size_t)h->d.N * sizeof(float), cudaMemcpyDefault, h->stream));
 	CK(cudaStreamSynchronize(h->stream));
 	return PQP_OK;
 }
@@ -942,6 +1036,7 @@ static int recover_on_device(pqp_handle *h, const float *Ydev, int ldy, const fl
 int pqp_recover_primal(pqp_handle *h, const float *Y, const float *Fp, int B, float *U)
 {
 	if (!h || !Y || !U || B <= 0) return PQP_ERR_INVALID;
+	env_scope scope(h);
 	CK(cudaSetDevice(h->device));
 	if (B > h->cap) {
 		/* growing the workspace would drop the cached Fp; only legal when the caller supplies Fp */
@@ -960,6 +1055,7 @@ int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B,
 			   float *U, pqp_status *st)
 {
 	if (!h || B <= 0 || !U) return PQP_ERR_INVALID;
+	env_scope scope(h);
 	CK(cudaSetDevice(h->device));
 	int rc = ensure_capacity(h, B);
 	if (rc) return rc;
@@ -974,6 +1070,7 @@ int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B,
 int pqp_shift_duals(pqp_handle *h, const float *Y, int B, float y_floor, float *Ynext)
 {
 	if (!h || !Y || !Ynext || B <= 0) return PQP_ERR_INVALID;
+	env_scope scope(h);
 	const int N = h->d.N, pH = h->d.pHorizon, nI = h->d.nInput;
 	if (pH <= 0 || nI <= 0 || 4 * pH * nI != N) return PQP_ERR_INVALID; /* not an MPC-structured dual */
 	CK(cudaSetDevice(h->device));
@@ -1020,6 +1117,104 @@ done:
 	if (dQn) cudaFree(dQn);
 	if (dv) cudaFree(dv);
 	return rc;
+}
+
+/* ---- stateless reference helpers on the device (what the compat library's computeFp / computeCost / convertToDual(Md) /
+ * computeUfromY call: no host arithmetic anywhere in the product) ------------------------------------------------------------- */
+struct dev_scratch {
+	float *p[8];
+	int n;
+	dev_scratch() : n(0) { memset(p, 0, sizeof p); }
+	~dev_scratch()
+	{
+		for (int i = 0; i < n; i++)
+			if (p[i]) cudaFree(p[i]);
+	}
+	/* device buffer of `count` floats, filled from `src` (host or device) when src != NULL */
+	float *get(size_t count, const float *src, int *rc)
+	{
+		float *d = NULL;
+		if (*rc) return NULL;
+		if ((*rc = dalloc(&d, count))) return NULL;
+		p[n++] = d;
+		if (src && cudaMemcpy(d, src, count * sizeof(float), cudaMemcpyDefault) != cudaSuccess) {
+			snprintf(g_cuda_err, sizeof g_cuda_err, "upload of %zu floats failed", count);
+			cudaGetLastError();
+			*rc = PQP_ERR_CUDA;
+		}
+		return d;
+	}
+};
+
+static int finish_stateless(const char *what, cudaError_t e, float *dst, const float *src_dev, size_t count)
+{
+	if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+	if (e == cudaSuccess) e = cudaMemcpy(dst, src_dev, count * sizeof(float), cudaMemcpyDefault);
+	if (e != cudaSuccess) {
+		snprintf(g_cuda_err, sizeof g_cuda_err, "%s -> %s", what, cudaGetErrorString(e));
+		cudaGetLastError();
+		return PQP_ERR_CUDA;
+	}
+	return PQP_OK;
+}
+
+int pqp_compute_fp(float *Fp, const float *Fp1, const float *Fp2, const float *Fp3, const float *D, const float *x, int M, int nDisH, int nState,
+		   int device)
+{
+	if (!Fp || !Fp3 || M <= 0 || nDisH < 0 || nState < 0 || (nDisH > 0 && (!Fp1 || !D)) || (nState > 0 && (!Fp2 || !x))) return PQP_ERR_INVALID;
+	if (pqp_device_count() == 0) return PQP_ERR_NO_DEVICE;
+	if (device >= 0) CK(cudaSetDevice(device));
+	dev_scratch sc;
+	int rc = PQP_OK;
+	float *dFp = sc.get((size_t)M, NULL, &rc), *d1 = sc.get((size_t)M * (nDisH > 0 ? nDisH : 1), nDisH > 0 ? Fp1 : NULL, &rc),
+	      *d2 = sc.get((size_t)M * (nState > 0 ? nState : 1), nState > 0 ? Fp2 : NULL, &rc), *d3 = sc.get((size_t)M, Fp3, &rc),
+	      *dD = sc.get((size_t)(nDisH > 0 ? nDisH : 1), nDisH > 0 ? D : NULL, &rc), *dx = sc.get((size_t)(nState > 0 ? nState : 1), nState > 0 ? x : NULL, &rc);
+	if (rc) return rc;
+	if (nState == 0) { /* the kernel reads "nState == 0" as "Fp is a constant": keep computeFp's formula with an empty x term */
+		CK(cudaMemset(dx, 0, sizeof(float)));
+		CK(cudaMemset(d2, 0, (size_t)M * sizeof(float)));
+		nState = 1;
+	}
+	return finish_stateless("pqp_compute_fp", pqp_launch_fp(dFp, d1, d2, d3, NULL, dD, 0, dx, 1, M, nDisH, nState, 0), Fp, dFp, (size_t)M);
+}
+
+int pqp_compute_cost(float *J, const float *Z, const float *Q, const float *F, const float *Mc, int N, int device)
+{
+	if (!J || !Z || !Q || !F || N <= 0) return PQP_ERR_INVALID;
+	if (pqp_device_count() == 0) return PQP_ERR_NO_DEVICE;
+	if (device >= 0) CK(cudaSetDevice(device));
+	dev_scratch sc;
+	int rc = PQP_OK;
+	float *dz = sc.get((size_t)N, Z, &rc), *dQ = sc.get((size_t)N * N, Q, &rc), *dF = sc.get((size_t)N, F, &rc), *dm = sc.get(1, Mc, &rc),
+	      *dt = sc.get((size_t)N, NULL, &rc), *dJ = sc.get(1, NULL, &rc);
+	if (rc) return rc;
+	return finish_stateless("pqp_compute_cost", pqp_launch_quad_form(dJ, dt, dz, dQ, dF, Mc ? dm : NULL, N, 0, 0), J, dJ, 1);
+}
+
+int pqp_compute_md(float *Md, const float *Fp, const float *Qp_inv, const float *Mp, int M, int device)
+{
+	if (!Md || !Fp || !Qp_inv || M <= 0) return PQP_ERR_INVALID;
+	if (pqp_device_count() == 0) return PQP_ERR_NO_DEVICE;
+	if (device >= 0) CK(cudaSetDevice(device));
+	dev_scratch sc;
+	int rc = PQP_OK;
+	float *dz = sc.get((size_t)M, Fp, &rc), *dQ = sc.get((size_t)M * M, Qp_inv, &rc), *dm = sc.get(1, Mp, &rc), *dt = sc.get((size_t)M, NULL, &rc),
+	      *dJ = sc.get(1, NULL, &rc);
+	if (rc) return rc;
+	return finish_stateless("pqp_compute_md", pqp_launch_quad_form(dJ, dt, dz, dQ, NULL, Mp ? dm : NULL, M, 1, 0), Md, dJ, 1);
+}
+
+int pqp_compute_u_from_y(float *U, const float *Y, const float *Fp, const float *Gp, const float *Qp_inv, int N, int M, int B, int device)
+{
+	if (!U || !Y || !Fp || !Gp || !Qp_inv || N <= 0 || M <= 0 || B <= 0) return PQP_ERR_INVALID;
+	if (pqp_device_count() == 0) return PQP_ERR_NO_DEVICE;
+	if (device >= 0) CK(cudaSetDevice(device));
+	dev_scratch sc;
+	int rc = PQP_OK;
+	float *dY = sc.get((size_t)B * N, Y, &rc), *dFp = sc.get((size_t)B * M, Fp, &rc), *dG = sc.get((size_t)N * M, Gp, &rc),
+	      *dQi = sc.get((size_t)M * M, Qp_inv, &rc), *dT = sc.get((size_t)B * M, NULL, &rc), *dU = sc.get((size_t)B * M, NULL, &rc);
+	if (rc) return rc;
+	return finish_stateless("pqp_compute_u_from_y", pqp_launch_recover(dU, dT, dY, N, dFp, dG, dQi, B, N, M, 1, 0), U, dU, (size_t)B * M);
 }
 
 /* ---- matrixMultiply (PQP_CPU.c:84-147) on the device ---------------------------------------- */
@@ -1109,6 +1304,7 @@ float pqp_last_solve_ms(pqp_handle *h)
 	return ms;
 }
 
+float pqp_setup_gemm_ms(pqp_handle *h) { return h ? h->setup_gemm_ms : -1.0f; }
 long long pqp_launch_count(pqp_handle *h) { return h ? h->launches : 0; }
 const char *pqp_last_kernel(pqp_handle *h) { return h ? h->last_kernel : "none"; }
 const float *pqp_device_qd(pqp_handle *h, int *ld)

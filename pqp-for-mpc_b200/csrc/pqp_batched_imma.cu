@@ -576,7 +576,7 @@ void pqp_imma_geometry(int N, int *MT, int *NKS, int *ksc)
 {
 	int nks = (N + 31) / 32;
 	int k = nks >= 3 ? 3 : 1;
-	if (getenv("PQP_IMMA_KSC") && atoi(getenv("PQP_IMMA_KSC")) == 1) k = 1;
+	if (pqp_env("PQP_IMMA_KSC") && atoi(pqp_env("PQP_IMMA_KSC")) == 1) k = 1;
 	*ksc = k;
 	*NKS = (nks + k - 1) / k * k;
 	*MT = (N + 127) / 128;
@@ -609,12 +609,12 @@ static cudaError_t launch_imma(const BiParams &p0, int cluster, size_t smem_opti
 			    (size_t)(4 * NB) * 5 * sizeof(float) /* evaluation partials [EW][PW][5], EW*PW = 4*NB */;
 	/* two plane buffers when at least three ring stages still fit beside them */
 	p.dbuf = (2 * pbuf + misc + 3 * (stage_bytes + 16) + 1024 <= smem_optin) ? 1 : 0;
-	if (getenv("PQP_IMMA_DBUF")) p.dbuf = p.dbuf && atoi(getenv("PQP_IMMA_DBUF")) != 0;
+	if (pqp_env("PQP_IMMA_DBUF")) p.dbuf = p.dbuf && atoi(pqp_env("PQP_IMMA_DBUF")) != 0;
 	const size_t fixed = (p.dbuf ? 2 : 1) * pbuf + misc;
 	int stages = (int)((smem_optin - 1024 - fixed) / (stage_bytes + 16));
 	if (stages > 16) stages = 16;
-	if (getenv("PQP_IMMA_STAGES")) {
-		const int v = atoi(getenv("PQP_IMMA_STAGES"));
+	if (pqp_env("PQP_IMMA_STAGES")) {
+		const int v = atoi(pqp_env("PQP_IMMA_STAGES"));
 		if (v >= 2 && v <= stages) stages = v;
 	}
 	if (stages < 2) return cudaErrorInvalidConfiguration;
@@ -659,7 +659,7 @@ cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, 
 	p.iters = iters;
 	pqp_imma_geometry(N, &p.MT, &p.NKS, &p.ksc);
 	p.b_sbo = (uint32_t)(p.NKS * 32) * 16u;
-	p.dbg = getenv("PQP_IMMA_DBG") ? atoi(getenv("PQP_IMMA_DBG")) : 0;
+	p.dbg = pqp_env("PQP_IMMA_DBG") ? atoi(pqp_env("PQP_IMMA_DBG")) : 0;
 	if (iters <= 0) {
 		if (!tolp || !tolp->status) return cudaErrorInvalidValue;
 		p.iters = 0;
@@ -677,7 +677,7 @@ cudaError_t pqp_launch_batched_imma(const void *tiles, const void *rowc, int N, 
 	}
 	/* PW = problems per epilogue thread: 8 doubles the epilogue warps of the 32-problem tile (16 instead of 8), which is what
 	 * hides the latency of its dependent fp32 chain (division, conversions) behind the tensor pipe */
-	const int pw = getenv("PQP_IMMA_PW") ? atoi(getenv("PQP_IMMA_PW")) : 8;
+	const int pw = pqp_env("PQP_IMMA_PW") ? atoi(pqp_env("PQP_IMMA_PW")) : 8;
 	cudaError_t e;
 	if (iters <= 0) e = launch_imma<32, 8, true>(p, cluster, smem_optin, s);
 	else if (nb == 64) e = launch_imma<64, 16, false>(p, cluster, smem_optin, s);

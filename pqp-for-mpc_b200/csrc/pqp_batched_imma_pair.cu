@@ -423,7 +423,7 @@ cudaError_t pqp_launch_batched_imma_pair(const void *tiles, const void *rowc, in
 	p.iters = iters;
 	pqp_imma_geometry(N, &p.MT, &p.NKS, &p.ksc);
 	p.b_sbo = (uint32_t)(p.NKS * 32) * 16u;
-	p.dbg = getenv("PQP_IMMA_DBG") ? atoi(getenv("PQP_IMMA_DBG")) : 0;
+	p.dbg = pqp_env("PQP_IMMA_DBG") ? atoi(pqp_env("PQP_IMMA_DBG")) : 0;
 	if (iters <= 0 || !pqp_batched_imma_pair_supported(N)) return cudaErrorInvalidValue;
 
 	const size_t pbuf = 3 * (size_t)(BP_NB / 16) * p.b_sbo;
@@ -431,8 +431,8 @@ cudaError_t pqp_launch_batched_imma_pair(const void *tiles, const void *rowc, in
 	const size_t misc = 3 * BP_NB * sizeof(uint32_t) + 96;
 	int stages = (int)((smem_optin - 1024 - pbuf - misc) / (stage_bytes + 16));
 	if (stages > 16) stages = 16;
-	if (getenv("PQP_IMMA_STAGES")) {
-		const int v = atoi(getenv("PQP_IMMA_STAGES"));
+	if (pqp_env("PQP_IMMA_STAGES")) {
+		const int v = atoi(pqp_env("PQP_IMMA_STAGES"));
 		if (v >= 2 && v <= stages) stages = v;
 	}
 	if (stages < 2) return cudaErrorInvalidConfiguration;

@@ -318,7 +318,7 @@ cudaError_t pqp_launch_batched_umma(const void *tiles, int N, int B, const float
 	p.MT = (N + 127) / 128;
 	p.NKC = (N + BU_KC - 1) / BU_KC;
 	p.b_sbo = (uint32_t)(p.NKC * BU_KC / 4) * BU_B_LBO;
-	p.dbg = getenv("PQP_UMMA_DBG") ? atoi(getenv("PQP_UMMA_DBG")) : 0;
+	p.dbg = pqp_env("PQP_UMMA_DBG") ? atoi(pqp_env("PQP_UMMA_DBG")) : 0;
 	const size_t smem = (size_t)BU_STAGES * BU_CHUNK + 2 * 4 * (size_t)p.b_sbo + (2 * BU_STAGES + 2) * sizeof(uint64_t) + 16;
 	cudaError_t e = cudaFuncSetAttribute(batched_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;

@@ -10,10 +10,14 @@
  *
  * Order of arithmetic: pqp_compat_set_order(PQP_ORDER_STRICT) makes every result bit-identical
  * to PQP_CPU.c; the default PQP_ORDER_FAST is within 1e-5 (normwise) of it.
+ *
+ * Nothing is computed on the host here: every function forwards to a device entry point of libpqp_b200.so.
+ * Stop test (g_fixed_iters == 0): the fused test on g = Qd y + Fd with the caller's Kp and Md -- terminate()'s
+ * three conditions (PQP_CPU.c:673-687) without forming Jp; its first condition (Jp <= -Jd, no tolerance) is met by the
+ * reference on rounding noise, so stop counts agree statistically, not exactly.
  */
 #include "pqp.h"
 
-#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -49,14 +53,9 @@ static pqp_opts opts_now(void)
 /* PQP_CPU.c:373 */
 void computeFp(float *Fp, float *Fp1, float *Fp2, float *Fp3, float *D, float *x)
 {
-	/* M-vector: computed here on the host in the reference's own order (it is 3 tiny products) */
-	const int M = g_dims.M, nd = g_dims.nDisH, nS = g_dims.nState;
-	for (int i = 0; i < M; i++) {
-		float t1 = 0.0f, t2 = 0.0f;
-		for (int k = 0; k < nd; k++) t1 += Fp1[i * nd + k] * D[k];
-		for (int k = 0; k < nS; k++) t2 += Fp2[i * nS + k] * x[k];
-		Fp[i] = (t1 + t2) + (-1.0f * Fp3[i]);
-	}
+	/* sizes come from #defines in the reference (PQP_CPU.c:13-17): pqp_compat_set_dims().  On the device, reference order. */
+	int rc = pqp_compute_fp(Fp, Fp1, Fp2, Fp3, D, x, g_dims.M, g_dims.nDisH, g_dims.nState, -1);
+	if (rc) complain("computeFp/pqp_compute_fp", rc);
 }
 
 /* PQP_CPU.c:489.  Qd/Fd/Md out; Qp_inv [M x M], Gp [N x M], Kp [N], Fp [M], Mp [1] in. */
@@ -77,41 +76,34 @@ void convertToDual(float *Qd, float *Fd, float *Md, float *Qp_inv, float *Gp, fl
 	if (rc) complain("convertToDual/pqp_get_dual", rc);
 	/* Fd = GQ*Fp + Kp is formed by the solve entry point: run one update on a scratch y, read Fd back */
 	float *ytmp = (float *)malloc(sizeof(float) * (size_t)N);
-	pqp_status st;
-	rc = pqp_solve_batch(h, NULL, NULL, 1, 1, NULL, ytmp, &st);
+	rc = pqp_solve_batch(h, NULL, NULL, 1, 1, NULL, ytmp, NULL);
 	if (rc) complain("convertToDual/pqp_solve_batch", rc);
 	else rc = pqp_get_linear_terms(h, 1, Fd, NULL);
 	if (rc) complain("convertToDual/pqp_get_linear_terms", rc);
 	free(ytmp);
-	if (Md) {
-		/* Md = Fp' Qp_inv Fp - Mp (PQP_CPU.c:472-479), reference order on the host: O(M^2) once */
-		float acc = 0.0f;
-		float *t = (float *)calloc((size_t)M, sizeof(float));
-		for (int j = 0; j < M; j++) {
-			float s = 0.0f;
-			for (int k = 0; k < M; k++) s += Fp[k] * Qp_inv[(size_t)k * M + j];
-			t[j] = s;
-		}
-		for (int j = 0; j < M; j++) acc += t[j] * Fp[j];
-		free(t);
-		Md[0] = acc - (Mp ? Mp[0] : 0.0f);
-	}
 	pqp_destroy(h);
+	if (Md) { /* Md = Fp' Qp_inv Fp - Mp (computeMd, PQP_CPU.c:472-479): on the device, reference order */
+		rc = pqp_compute_md(Md, Fp, Qp_inv, Mp, M, -1);
+		if (rc) complain("convertToDual/pqp_compute_md", rc);
+	}
 }
 
 /* PQP_CPU.c:694.  Y out [N], U out [M] (the last computeUfromY of terminate, PQP_CPU.c:675). */
 void solveQuadraticDual(float *Y, float *Qd, float *Fd, float *Md, float *U, float *Qp, float *Qp_inv, float *Fp,
 			float *Mp, float *Gp, float *Kp, int N, int M)
 {
-	(void)Qp; (void)Mp; (void)Kp; (void)Md;
+	(void)Qp; (void)Mp; /* Jp is never formed: Jp + Jd = y'(Qd y + Fd), so Gauss_Jordan's Qp and Mp are not needed */
 	pqp_opts o = opts_now();
 	pqp_handle *h = NULL;
 	int rc = pqp_setup_dual(&h, N, Qd, M, Gp, Qp_inv, &o);
 	if (rc) { complain("solveQuadraticDual/pqp_setup_dual", rc); return; }
+	/* the caller's Kp and Md reach the stop test: compare()'s per-row tolerance max(erc*Kp_i, eac) (PQP_CPU.c:338) and the
+	 * scale of the relative gap test |Jp + Jd| <= erj*|Jd| with Jd including Md/2 (PQP_CPU.c:684, :661) */
+	if (Kp && (rc = pqp_set_constraint_bounds(h, Kp))) complain("solveQuadraticDual/pqp_set_constraint_bounds", rc);
 	pqp_status st;
 	memset(&st, 0, sizeof st);
-	rc = pqp_solve_dual(h, Fd, 1, (int)g_fixed_iters, NULL, Y, &st);
-	if (rc) complain("solveQuadraticDual/pqp_solve_dual", rc);
+	rc = pqp_solve_dual_full(h, Fd, Md, 1, (int)g_fixed_iters, NULL, Y, &st);
+	if (rc) complain("solveQuadraticDual/pqp_solve_dual_full", rc);
 	else if (U && Fp && Gp && Qp_inv) {
 		rc = pqp_recover_primal(h, Y, Fp, 1, U);
 		if (rc) complain("solveQuadraticDual/pqp_recover_primal", rc);
@@ -124,36 +116,16 @@ void solveQuadraticDual(float *Y, float *Qd, float *Fd, float *Md, float *U, flo
 /* PQP_CPU.c:352 */
 void computeUfromY(float *U, float *Y, float *Fp, float *Gp, float *Qp_inv, int N, int M)
 {
-	/* a handle is built around a dual Hessian; recovery never reads it, so it gets N x N zeros */
-	pqp_opts o = opts_now();
-	pqp_handle *h = NULL;
-	float *Qz = (float *)calloc((size_t)N * N, sizeof(float));
-	if (!Qz) { complain("computeUfromY", PQP_ERR_ALLOC); return; }
-	int rc = pqp_setup_dual(&h, N, Qz, M, Gp, Qp_inv, &o);
-	free(Qz);
-	if (rc) { complain("computeUfromY/pqp_setup_dual", rc); return; }
-	rc = pqp_recover_primal(h, Y, Fp, 1, U);
-	if (rc) complain("computeUfromY/pqp_recover_primal", rc);
-	pqp_destroy(h);
+	int rc = pqp_compute_u_from_y(U, Y, Fp, Gp, Qp_inv, N, M, 1, -1);
+	if (rc) complain("computeUfromY/pqp_compute_u_from_y", rc);
 }
 
-/* PQP_CPU.c:648: J = 1/2 z'Qz + F'z + m/2.  O(n^2) scalar on the host, reference order. */
+/* PQP_CPU.c:648: J = 1/2 z'Qz + F'z + m/2, on the device in the reference's order and promotions */
 float computeCost(float *Z, float *Q, float *F, float *M, int N)
 {
 	float J = 0;
-	float *t = (float *)calloc((size_t)N, sizeof(float));
-	for (int j = 0; j < N; j++) {
-		float s = 0.0f;
-		for (int k = 0; k < N; k++) s += Z[k] * Q[(size_t)k * N + j];
-		t[j] = s;
-	}
-	float q = 0.0f, l = 0.0f;
-	for (int j = 0; j < N; j++) q += t[j] * Z[j];
-	for (int j = 0; j < N; j++) l += F[j] * Z[j];
-	free(t);
-	J += 0.5 * q;
-	J += l;
-	J += M[0] / 2;
+	int rc = pqp_compute_cost(&J, Z, Q, F, M, N, -1);
+	if (rc) complain("computeCost/pqp_compute_cost", rc);
 	return J;
 }
 

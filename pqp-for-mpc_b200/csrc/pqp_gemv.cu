@@ -357,11 +357,9 @@ __global__ void __launch_bounds__(128) gemv_strict_kernel(const float *__restric
 cudaError_t pqp_launch_gemv_strict_step(const pqp_gemv_args *a, const float *y_in, float *y_out, cudaStream_t s)
 {
 	const size_t smem = sizeof(float) * (size_t)a->N;
-	static int configured = 0;
-	if (!configured) {
+	if (smem > 48 * 1024) { /* per device and context, so set on every launch that needs it (a cheap host-side call) */
 		cudaError_t e = cudaFuncSetAttribute(gemv_strict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		if (e != cudaSuccess) return e;
-		configured = 1;
 	}
 	gemv_strict_kernel<<<(a->N + 127) / 128, 128, smem, s>>>(a->QT, a->ldq, a->N, a->theta, a->Fd, y_in, y_out);
 	return cudaGetLastError();

@@ -1113,16 +1113,16 @@ cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, 
 	g.rows_max = (a->N + a->grid - 1) / a->grid + 1;
 	g.pol_keep = 2;
 	g.pol_stream = 1;
-	if (getenv("PQP_POL_KEEP")) g.pol_keep = atoi(getenv("PQP_POL_KEEP"));
-	if (getenv("PQP_POL_STREAM")) g.pol_stream = atoi(getenv("PQP_POL_STREAM"));
+	if (pqp_env("PQP_POL_KEEP")) g.pol_keep = atoi(pqp_env("PQP_POL_KEEP"));
+	if (pqp_env("PQP_POL_STREAM")) g.pol_stream = atoi(pqp_env("PQP_POL_STREAM"));
 	g.pk0 = reinterpret_cast<uint2 *>(pk0);
 	g.pk1 = reinterpret_cast<uint2 *>(pk1);
 	g.rowpart = reinterpret_cast<uint4 *>(pl->rowpart);
 	g.colpart = reinterpret_cast<uint4 *>(pl->colpart);
-	g.dbg_ = getenv("PQP_SYM_DBG") ? atoi(getenv("PQP_SYM_DBG")) : 0; /* honoured only when built with -DPQP_SYM_DEBUG */
+	g.dbg_ = pqp_env("PQP_SYM_DBG") ? atoi(pqp_env("PQP_SYM_DBG")) : 0; /* honoured only when built with -DPQP_SYM_DEBUG */
 	g.prof = NULL;
 	static long long *prof_dev = NULL;
-	const int prof = getenv("PQP_SYM_PROF") && atoi(getenv("PQP_SYM_PROF"));
+	const int prof = pqp_env("PQP_SYM_PROF") && atoi(pqp_env("PQP_SYM_PROF"));
 	if (prof) {
 		if (!prof_dev) cudaMalloc((void **)&prof_dev, sizeof(long long) * 4 * 256);
 		cudaMemsetAsync(prof_dev, 0, sizeof(long long) * 4 * 256, s);
@@ -1162,7 +1162,7 @@ cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, 
 				if (v > mx[k]) mx[k] = v;
 				if (v < mn[k]) mn[k] = v;
 			}
-		if (atoi(getenv("PQP_SYM_PROF")) > 1)
+		if (atoi(pqp_env("PQP_SYM_PROF")) > 1)
 			for (int c = 0; c < a->grid; c++)
 				fprintf(stderr, "cta %3d: y %6.0f units %6.0f owner %6.0f\n", c, (double)hp[c * 4] / (a->iters > 0 ? a->iters : 1), (double)hp[c * 4 + 1] / (a->iters > 0 ? a->iters : 1),
 					(double)hp[c * 4 + 2] / (a->iters > 0 ? a->iters : 1));

@@ -593,8 +593,8 @@ cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident
 	g.rows_max = (a->N + a->grid - 1) / a->grid + 1;
 	/* eight rows per slab parked in tensor memory: long-row instantiation only, and only when something is streamed at all */
 	g.tmem_rows = (yc == 4 && g.rows_max <= TMA_TM_ROWS_MAX && resident < g.rows_max) ? 8 : 0;
-	if (getenv("PQP_TMA_TMEM")) {
-		const int v = atoi(getenv("PQP_TMA_TMEM"));
+	if (pqp_env("PQP_TMA_TMEM")) {
+		const int v = atoi(pqp_env("PQP_TMA_TMEM"));
 		if (v >= 0 && v <= 8 && g.tmem_rows) g.tmem_rows = v;
 	}
 	g.pol_keep = 2;
@@ -606,8 +606,8 @@ cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident
 		if (e0 == cudaSuccess) e0 = cudaMemsetAsync(pk1, 0xFF, (size_t)a->ldq * sizeof(uint2), s);
 		if (e0 != cudaSuccess) return e0;
 	}
-	if (getenv("PQP_POL_KEEP")) g.pol_keep = atoi(getenv("PQP_POL_KEEP"));
-	if (getenv("PQP_POL_STREAM")) g.pol_stream = atoi(getenv("PQP_POL_STREAM"));
+	if (pqp_env("PQP_POL_KEEP")) g.pol_keep = atoi(pqp_env("PQP_POL_KEEP"));
+	if (pqp_env("PQP_POL_STREAM")) g.pol_stream = atoi(pqp_env("PQP_POL_STREAM"));
 	const size_t smem = tma_smem_bytes(a->ldq, g);
 	const void *fn = NULL;
 	switch (yc) {

@@ -16,6 +16,14 @@
 
 static inline int pqp_round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+/*
+ * Experiment knobs (PQP_* environment variables) are read ONCE per handle, when it is created: pqp_setup /
+ * pqp_setup_dual snapshot every PQP_* variable into the handle, each public entry point makes its handle's snapshot the calling
+ * thread's current one, and every kernel-selection / geometry decision asks pqp_env() -- no getenv() on the solve path.
+ * Outside a handle (pqp_matmul and the other stateless helpers) pqp_env() reads the process environment.
+ */
+const char *pqp_env(const char *name);
+
 /* ---- setup kernels (pqp_setup_kernels.cu) ------------------------------------------------ */
 /* C[a x c] (ldc) = A[a x b] (lda) * op(B); transB: B stored [c x b] (ldb) else [b x c] (ldb).
  * strict: one thread per element, k ascending, separately rounded mul/add (PQP_CPU.c:84-147). */
@@ -56,6 +64,10 @@ cudaError_t pqp_launch_shift_duals(float *out, const float *in, int B, int pH, i
 /* Yn = Y .* (Qn*Y + Fdn) ./ (Qp*Y + Fdp), reference order (updateY2 + updY); all device pointers */
 cudaError_t pqp_launch_update_y2_dense(float *Yn, const float *Y, const float *Qp, const float *Qn, const float *Fdp, const float *Fdn, int N,
 				       cudaStream_t s);
+/* mode 0: out[0] = 1/2 z'Az + F'z + m/2 (computeCost, PQP_CPU.c:648-666); mode 1: out[0] = z'Az - m (computeMd, :472-479);
+ * reference order and promotions; tmp [n] scratch; all device pointers */
+cudaError_t pqp_launch_quad_form(float *out, float *tmp, const float *z, const float *A, const float *F, const float *m, int n, int mode,
+				 cudaStream_t s);
 /* fill n floats */
 cudaError_t pqp_launch_fill(float *p, float v, size_t n, cudaStream_t s);
 
@@ -115,9 +127,10 @@ cudaError_t pqp_launch_build_sym_units(float *units, const float *Q, int ldq, in
 cudaError_t pqp_launch_gemv_sym(const pqp_gemv_args *a, const pqp_sym_plan *pl, void *pk0, void *pk1, cudaStream_t s);
 /* strict: one launch per iteration, thread i owns row i and walks k ascending over QT */
 cudaError_t pqp_launch_gemv_strict_step(const pqp_gemv_args *a, const float *y_in, float *y_out, cudaStream_t s);
-/* evaluation of the status quantities for one y (any mode) */
+/* evaluation of the status quantities for one y (any mode); viol_out [B] (device, may be NULL) receives
+ * max_i(-g_i - max(erc*Kp_i, eac)), the quantity compare() tests per row (PQP_CPU.c:334-343): feasible iff <= 0 */
 cudaError_t pqp_launch_status(pqp_status *st, const float *Q, int ldq, int N, const float *Y, int ldy, const float *Fd,
-			      const float *Md, const float *Kp, float erc, float eac, int B, int iters, cudaStream_t s);
+			      const float *Md, const float *Kp, float erc, float eac, int B, int iters, float *viol_out, cudaStream_t s);
 
 /* ---- batched iteration (pqp_batched.cu) ------------------------------------------------------ */
 /* k-major pre-split operands: QpT/QnT [Kpad x Ipad], [k][i] = max(0,+-Qd[i][k]) + theta_i*(i==k) */

@@ -415,7 +415,7 @@ cudaError_t pqp_launch_fill(float *p, float v, size_t n, cudaStream_t s)
 __global__ void __launch_bounds__(256)
 status_kernel(pqp_status *__restrict__ st, const float *__restrict__ Q, int ldq, int N, const float *__restrict__ Y, int ldy,
 	      const float *__restrict__ Fd, const float *__restrict__ Md, const float *__restrict__ Kp, float erc, float eac,
-	      int iters)
+	      int iters, float *__restrict__ viol_out)
 {
 	__shared__ float r_min[8], r_gap[8], r_jd[8], r_kkt[8], r_viol[8];
 	const int b = blockIdx.x, warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -452,13 +452,15 @@ status_kernel(pqp_status *__restrict__ st, const float *__restrict__ Q, int ldq,
 		o.Jd = jd + (Md ? 0.5f * Md[b] : 0.0f);
 		o.kkt = kkt;
 		st[b] = o;
+		/* max_i(-g_i - max(erc*Kp_i, eac)): <= 0 is checkFeas/compare passing (PQP_CPU.c:632-641, :334-343) */
+		if (viol_out) viol_out[b] = viol;
 	}
 }
 
 cudaError_t pqp_launch_status(pqp_status *st, const float *Q, int ldq, int N, const float *Y, int ldy, const float *Fd,
-			      const float *Md, const float *Kp, float erc, float eac, int B, int iters, cudaStream_t s)
+			      const float *Md, const float *Kp, float erc, float eac, int B, int iters, float *viol_out, cudaStream_t s)
 {
-	status_kernel<<<B, 256, 0, s>>>(st, Q, ldq, N, Y, ldy, Fd, Md, Kp, erc, eac, iters);
+	status_kernel<<<B, 256, 0, s>>>(st, Q, ldq, N, Y, ldy, Fd, Md, Kp, erc, eac, iters, viol_out);
 	return cudaGetLastError();
 }
 
@@ -535,5 +537,45 @@ cudaError_t pqp_launch_update_y2_dense(float *Yn, const float *Y, const float *Q
 				       cudaStream_t s)
 {
 	update_y2_dense_kernel<<<(N + 63) / 64, 64, 0, s>>>(Yn, Y, Qp, Qn, Fdp, Fdn, N);
+	return cudaGetLastError();
+}
+
+/* ---- computeCost (PQP_CPU.c:648-666) and computeMd (:472-479) in the reference's order ------------------------------------------
+ * Both start with the row vector t = z' A (matrixMultiply(tmp, Z, 1, Q, 0, 1, n, n): t_j = sum_k z_k A[k][j], k ascending from
+ * zero, separately rounded multiply and add) followed by the dot product t z (j ascending).  Thread j owns t_j (coalesced over
+ * j); one thread then walks the two dot products.  O(n^2) once per call; bit-identical to the reference. */
+__global__ void rowvec_mat_strict_kernel(float *__restrict__ t, const float *__restrict__ z, const float *__restrict__ A, int n)
+{
+	const int j = blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) return;
+	float acc = 0.0f;
+	for (int k = 0; k < n; k++) acc = __fadd_rn(acc, __fmul_rn(z[k], A[(size_t)k * n + j]));
+	t[j] = acc;
+}
+/* mode 0: J = 1/2 t z + F z + m/2 with the reference's promotions (0.5*tmp[0] is a double product rounded into the float J,
+ * M[0]/2 a float division); mode 1: Md = t z - m */
+__global__ void quad_finish_kernel(float *__restrict__ out, const float *__restrict__ t, const float *__restrict__ z,
+				   const float *__restrict__ F, const float *__restrict__ m, int n, int mode)
+{
+	if (blockIdx.x || threadIdx.x) return;
+	float q = 0.0f;
+	for (int j = 0; j < n; j++) q = __fadd_rn(q, __fmul_rn(t[j], z[j]));
+	if (mode == 1) {
+		out[0] = __fsub_rn(q, m ? m[0] : 0.0f);
+		return;
+	}
+	float J = 0.0f;
+	J = (float)((double)J + 0.5 * (double)q);
+	float l = 0.0f;
+	for (int j = 0; j < n; j++) l = __fadd_rn(l, __fmul_rn(F[j], z[j]));
+	J = __fadd_rn(J, l);
+	J = __fadd_rn(J, __fdiv_rn(m ? m[0] : 0.0f, 2.0f));
+	out[0] = J;
+}
+cudaError_t pqp_launch_quad_form(float *out, float *tmp, const float *z, const float *A, const float *F, const float *m, int n, int mode,
+				 cudaStream_t s)
+{
+	rowvec_mat_strict_kernel<<<(n + 127) / 128, 128, 0, s>>>(tmp, z, A, n);
+	quad_finish_kernel<<<1, 32, 0, s>>>(out, tmp, z, F, m, n, mode);
 	return cudaGetLastError();
 }
