@@ -36,3 +36,34 @@ def test_stdout_carries_only_the_json_line_even_if_a_library_prints():
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout == '{"ok": 1}\n', out.stdout
     assert "NCCL version x.y" in out.stderr and "library noise" in out.stderr
+
+
+def test_reference_arm_never_loads_the_product_library():
+    """`--impl reference` must time the reference's CPU code with none of the product in the process: the instance comes from the
+    numpy port of the generator / the oracle's own loader, so libpqp_b200.so is never mapped (round-1 review, item 9)."""
+    code = ("import sys, numpy as np; sys.argv = ['bench.py']; sys.path.insert(0, %r); import bench\n"
+            "class A: gpus = 1; steps = 1; warmup = 0; iters = 1000\n"
+            "bench._OUT = open('/dev/null', 'w')\n"
+            "bench.cpu_updates_for = lambda N, seconds=6.0: 2\n"
+            "for w in ('c1', 'c2', 'c4'):\n"
+            "    a = A(); a.iters = bench.WORKLOADS[w].get('iters', 1000); bench.run_reference(a, w, 0, 1)\n"
+            "maps = open('/proc/self/maps').read()\n"
+            "assert 'libpqp_b200' not in maps and 'libpqp_compat' not in maps, 'product library mapped'\n"
+            "assert 'libpqp_ref' in maps or 'libpqp_oracle' in maps\n"
+            "print('ok')") % ROOT
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]
+
+
+def test_default_reference_line_is_the_c5_metric():
+    """With no --workload the reference arm reports the top-level metric of the product arm: batched QP solves/s on config 5."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    code = ("import sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0']; sys.path.insert(0, %r); import bench\n"
+            "bench.cpu_parallel_rate = lambda engine, Qd, Fd, updates, threads: (100.0 * threads, updates / 100.0)\n"
+            "bench.main()") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip())
+    assert d["impl"] == "reference" and d["metric"] == "qp_solves_per_sec" and d["unit"] == "solves/s" and d["scaling"] == "strong"
+    assert d["config"]["workload"] == "c5" and d["config"]["B_total"] == 1 << 20 and d["config"]["N"] == 480

@@ -142,3 +142,34 @@ def test_product_never_references_the_oracle():
             if f.endswith((".c", ".cu", ".h", ".cuh", ".py")) or f == "Makefile":
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in src.lower(), (dirpath, f)
+
+
+def test_numpy_port_of_the_generator_is_bit_identical():
+    """bench_problems.generator_instance (what `bench.py --impl reference` uses, so that the CPU arm never loads the product
+    library) against pqp_generate_testproblem, element for element."""
+    import pqp_for_mpc_b200 as pqp
+    from bench_problems import generator_instance
+    for seed, M, N in ((12345, 512, 1024), (1, 1, 1), (7, 3, 5), (2**63 + 11, 40, 17)):
+        a, da = generator_instance(seed, M, N)
+        b, db = pqp.generate_testproblem(seed, M, N)
+        assert (da.M, da.N) == (db.M, db.N) == (M, N)
+        for k in ("Qp_inv", "Fp", "Kp", "Gp"):
+            assert np.array_equal(a[k], b[k]), (seed, k)
+        assert a["Mp0"] == b["Mp0"]
+
+
+def test_bench_states_are_seeded_and_clearly_constrained():
+    """bench_problems.condensed_mpc with the bench's state recipe: deterministic, shard-independent, and every state has at
+    least BENCH_MIN_VIOLATED rows of Fd(x) below -1 (no trivially-zero problem); the recipe with min_violated = 0 is the
+    round-1 stream unchanged."""
+    from bench_problems import BENCH_MIN_VIOLATED, BENCH_X_SCALE, condensed_mpc
+    p1, d1, X1 = condensed_mpc(2024, 6, 5, 2, n_states=3000, x_scale=BENCH_X_SCALE, min_violated=BENCH_MIN_VIOLATED)
+    p2, d2, X2 = condensed_mpc(2024, 6, 5, 2, n_states=3000, x_scale=BENCH_X_SCALE, min_violated=BENCH_MIN_VIOLATED)
+    assert np.array_equal(X1, X2) and (d1.M, d1.N, d1.nDisH) == (12, 48, 6)
+    GQ = p1["Gp"].astype(np.float64) @ p1["Qp_inv"].astype(np.float64)
+    Fp = (p1["Fp1"].astype(np.float64) @ p1["D"])[None] + X1.astype(np.float64) @ p1["Fp2"].T.astype(np.float64) - p1["Fp3"][None]
+    Fd = Fp @ GQ.T + p1["Kp"][None]
+    assert ((Fd < -0.99).sum(axis=1) >= BENCH_MIN_VIOLATED).all()
+    _, _, X3 = condensed_mpc(2024, 6, 5, 2, n_states=3000)
+    _, _, X4 = condensed_mpc(2024, 6, 5, 2, n_states=3000, x_scale=60.0, min_violated=0)
+    assert np.array_equal(X3, X4)
