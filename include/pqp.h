@@ -113,6 +113,12 @@ typedef struct pqp_opts {
 			       * not exactly symmetric.  pqp_setup (not pqp_setup_dual), FAST order: the Qd it
 			       * builds from Gp Qp_inv Gp' gets one value per pair (Q_ij, Q_ji) -- their mean -- when all pairs agree to
 			       * rounding (1e-5 sqrt(Q_ii Q_jj)), so a dense symmetric Qp_inv also reaches the upper-triangle loop */
+	int exploit_structure; /* FAST mode, batched loop: 1 (default) when the constraint rows come in +/- pairs as in the reference's
+			       * MPC layout (Gp = [G; -G] per half, N = 4*pHorizon*nInput, PQP_CPU.c:941), i.e. the fp32 Qd of the handle
+			       * satisfies Qd[i+N/4][j] == -Qd[i][j] == Qd[i][j+-N/4] element for element (tested once on the device), the
+			       * tensor-core loop multiplies only the N/2 representative rows and updates each row together with its
+			       * partner: the same exact integer sums, half the work.  0: always all N rows.  Never applies to a Qd
+			       * without that structure */
 } pqp_opts;
 
 /* Per-problem result of a solve (replaces the printf's of PQP_CPU.c:741,1005-1006). */

@@ -74,6 +74,8 @@ struct pqp_handle {
 	float *QpT, *QnT; /* batched operands, built on first batched solve */
 	void *umma_tiles; /* pre-split, pre-tiled tf32 hi/lo operand of the tcgen05 3xTF32 batched kernel */
 	void *imma_tiles, *imma_rowc; /* digit planes + row constants of the tcgen05 int8 (error-free) batched kernel */
+	void *imma_ptiles, *imma_prowc; /* the same for the PAIRED scheme (Qd with the +/- row-pair structure of an MPC dual) */
+	int paired_state; /* 0 not examined, 1 structure present and the arrays built, -1 unavailable */
 	int Kpad, Ipad;
 	/* per-batch workspace */
 	int cap;
@@ -122,6 +124,7 @@ void pqp_default_opts(pqp_opts *o)
 	o->use_tensor_cores = 1;
 	o->l2_persist = 1;
 	o->exploit_symmetry = 1;
+	o->exploit_structure = 1;
 }
 
 int pqp_output_offsets(const pqp_dims *d, const float *Z, const float *Theta, float *Kx, float *Kd)
@@ -563,7 +566,7 @@ void pqp_destroy(pqp_handle *h)
 		if (h->l2_limit_changed) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_limit_saved);
 	}
 	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
-			 h->Kx, h->Kd, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
+			 h->Kx, h->Kd, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->imma_ptiles, h->imma_prowc, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
 			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf, h->pk0, h->pk1,
 			 h->sym.units, h->sym.cta_u0, h->sym.cta_j0, h->sym.strip_c0, h->sym.strip_c1, h->sym.rowpart, h->sym.colpart };
 	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
@@ -821,6 +824,42 @@ static int ensure_imma_tiles(pqp_handle *h)
 	return PQP_OK;
 }
 
+/*
+ * The PAIRED batched scheme needs Qd[sigma(i)][j] == -Qd[i][j] == Qd[i][sigma(j)] element for element (pqp_batched_imma_pair.cu);
+ * examined once per handle, on the first batched solve that could use it.  Leaves h->paired_state at 1 or -1.
+ */
+static int ensure_imma_paired(pqp_handle *h)
+{
+	if (h->paired_state) return PQP_OK;
+	h->paired_state = -1;
+	const int N = h->d.N;
+	const char *e;
+	if ((e = pqp_env("PQP_IMMA_PAIRED")) && atoi(e) == 0) return PQP_OK;
+	if (!h->o.exploit_structure || h->o.order == PQP_ORDER_STRICT || !pqp_batched_imma_paired_supported(N)) return PQP_OK;
+	unsigned *bad_dev = NULL, bad = 1;
+	int rc;
+	if ((rc = dalloc(&bad_dev, 1))) return rc;
+	cudaError_t ce = pqp_launch_pair_struct_check(h->Q, h->ldq, N, bad_dev, h->stream);
+	h->launches++;
+	if (ce == cudaSuccess) ce = cudaMemcpyAsync(&bad, bad_dev, sizeof bad, cudaMemcpyDeviceToHost, h->stream);
+	if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+	cudaFree(bad_dev);
+	CK(ce);
+	if (pqp_env("PQP_VERBOSE")) fprintf(stderr, "pqp: +/- row-pair structure of Qd: %u violations\n", bad);
+	if (bad) return PQP_OK;
+	unsigned char *t = NULL, *r = NULL;
+	if ((rc = dalloc(&t, pqp_batched_imma_paired_tiles_bytes(N))) || (rc = dalloc(&r, pqp_batched_imma_paired_rowc_bytes(N)))) {
+		if (t) cudaFree(t);
+		return rc;
+	}
+	h->imma_ptiles = t;
+	h->imma_prowc = r;
+	CK(pqp_launch_build_imma_tiles_paired(h->imma_ptiles, h->imma_prowc, h->Q, h->ldq, h->theta, N, h->stream));
+	h->launches++;
+	h->paired_state = 1;
+	return PQP_OK;
+}
+
 static int ensure_umma_tiles(pqp_handle *h)
 {
 	if (h->umma_tiles) return PQP_OK;
@@ -882,8 +921,16 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			const int pair = iters > 0 && B > 32 && pqp_batched_imma_pair_supported(N) &&
 					 (pqp_env("PQP_IMMA_PAIR") ? atoi(pqp_env("PQP_IMMA_PAIR")) != 0 : 1);
 			if (pair) {
-				CK(pqp_launch_batched_imma_pair(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, h->smem_optin, h->stream));
-				h->last_kernel = "batched_imma_pair";
+				/* a Qd with the +/- row-pair structure of a box-constrained MPC dual: half the tensor work (PAIRED instantiation) */
+				int rc2 = ensure_imma_paired(h);
+				if (rc2) return rc2;
+				if (h->paired_state == 1) {
+					CK(pqp_launch_batched_imma_paired(h->imma_ptiles, h->imma_prowc, N, B, h->Fd, h->Y, iters, h->smem_optin, h->stream));
+					h->last_kernel = "batched_imma_paired";
+				} else {
+					CK(pqp_launch_batched_imma_pair(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, h->smem_optin, h->stream));
+					h->last_kernel = "batched_imma_pair";
+				}
 			} else {
 			pqp_imma_tol t;
 			t.max_iters = h->o.max_iters; t.check_every = h->o.check_every;

@@ -35,51 +35,6 @@
 #define BP_UNIT_COLS (3u * BP_NB)
 #define BP_MAX_MY 2     /* M tiles per CTA (N <= 512) */
 
-namespace {
-
-__device__ __forceinline__ uint32_t map_peer(uint32_t local_addr, uint32_t rank)
-{
-	uint32_t r;
-	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-	return r;
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v)
-{
-	asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void red_max_cluster(uint32_t addr, uint32_t v)
-{
-	asm volatile("red.relaxed.cluster.shared::cluster.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-/* arrive on an mbarrier of any CTA of the cluster (address from map_peer, or the own CTA's mapped address) */
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr)
-{
-	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
-}
-/* relaxed arrival; the caller has issued fence_release_cluster() after its writes */
-__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t addr)
-{
-	asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
-}
-__device__ __forceinline__ void fence_release_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
-{
-	asm volatile(
-		"{\n\t"
-		".reg .pred p;\n\t"
-		"PAIR_WAIT:\n\t"
-		"mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-		"@p bra PAIR_DONE;\n\t"
-		"bra PAIR_WAIT;\n\t"
-		"PAIR_DONE:\n\t"
-		"}" ::"r"(umma::smem_addr(bar)),
-		"r"(parity)
-		: "memory");
-}
-/* all state spaces: the remote (shared::cluster) digit stores must reach the peer's tensor core too */
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-} /* namespace */
 
 /*
  * shared memory: ring [stages][ksc*BI_CHUNK] | planes [3][4][Kpad/8][8][16 B] | smax[2][64] | iscale[64] | barriers

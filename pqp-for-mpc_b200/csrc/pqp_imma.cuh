@@ -219,6 +219,58 @@ __device__ __forceinline__ void digits4(int b0, int b1, int b2, int b3, uint32_t
 	w0 = __byte_perm(__byte_perm(d_0, d_1, 0x0051), __byte_perm(d_2, d_3, 0x0051), 0x5410);
 }
 
+/* ---- cluster (CTA pair) helpers: DSMEM stores / reductions / mbarrier arrivals on the peer ---- */
+__device__ __forceinline__ uint32_t map_peer(uint32_t local_addr, uint32_t rank)
+{
+	uint32_t r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+	return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v)
+{
+	asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void red_max_cluster(uint32_t addr, uint32_t v)
+{
+	asm volatile("red.relaxed.cluster.shared::cluster.max.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+/* arrive on an mbarrier of any CTA of the cluster (address from map_peer, or the own CTA's mapped address) */
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr)
+{
+	asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+/* relaxed arrival; the caller has issued fence_release_cluster() after its writes */
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t addr)
+{
+	asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void fence_release_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n\t"
+		".reg .pred p;\n\t"
+		"PAIR_WAIT:\n\t"
+		"mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+		"@p bra PAIR_DONE;\n\t"
+		"bra PAIR_WAIT;\n\t"
+		"PAIR_DONE:\n\t"
+		"}" ::"r"(umma::smem_addr(bar)),
+		"r"(parity)
+		: "memory");
+}
+/* all state spaces: the remote (shared::cluster) digit stores must reach the peer's tensor core too */
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t a, uint32_t b)
+{
+	asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_i32(uint32_t taddr, int *v)
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+
 } /* namespace */
 
 struct BiParams {

@@ -167,6 +167,15 @@ void pqp_imma_geometry(int N, int *MT, int *NKS, int *ksc);
 int pqp_batched_imma_pair_supported(int N);
 cudaError_t pqp_launch_batched_imma_pair(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters,
 					 size_t smem_optin, cudaStream_t s);
+/* the loop for a Qd with the +/- row-pair structure of a box-constrained MPC dual (pqp_batched_imma_paired.cu): half the tensor
+ * work, two interleaved groups of 32 problems per CTA pair; its own tile / row-constant arrays; fixed count only */
+int pqp_batched_imma_paired_supported(int N);
+size_t pqp_batched_imma_paired_tiles_bytes(int N);
+size_t pqp_batched_imma_paired_rowc_bytes(int N);
+cudaError_t pqp_launch_pair_struct_check(const float *Q, int ldq, int N, unsigned *bad, cudaStream_t s);
+cudaError_t pqp_launch_build_imma_tiles_paired(void *tiles, void *rowc, const float *Q, int ldq, const float *theta, int N, cudaStream_t s);
+cudaError_t pqp_launch_batched_imma_paired(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters,
+					   size_t smem_optin, cudaStream_t s);
 #define PQP_BATCH_KPAD 16
 #define PQP_BATCH_IPAD 128
 

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from conftest import active_set, relerr
-from imma_model import run as model_run
+from imma_model import has_pair_structure, run as model_run, run_paired as model_run_paired
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
@@ -28,11 +28,40 @@ def test_imma_is_bit_identical_to_its_model(pqp, pH, nS, nI, B, K):
     prob, d, X = _mpc(11, pH, nS, nI, B)
     with pqp.Solver(d, prob, batch_capacity=B) as s:
         Y, _, _ = s.solve(X, iters=K, status=False)
-        assert s.last_kernel in ("batched_imma", "batched_imma_pair")
+        assert s.last_kernel in ("batched_imma", "batched_imma_pair", "batched_imma_paired")
+        kernel = s.last_kernel
         Qd, th, _ = s.dual()
         Fd, _ = s.linear_terms(B, want_fp=False)
     n = min(B, 40)
-    assert np.array_equal(Y[:n], model_run(Qd, th, Fd[:n], K), equal_nan=True)
+    model = model_run_paired if kernel == "batched_imma_paired" else model_run
+    assert np.array_equal(Y[:n], model(Qd, th, Fd[:n], K), equal_nan=True)
+
+
+@pytest.mark.parametrize("pH,nS,nI,B,K", [(30, 12, 4, 130, 150), (17, 4, 4, 97, 40), (13, 3, 5, 64, 30), (32, 4, 4, 33, 20), (16, 4, 4, 70, 25)])
+def test_paired_rows_kernel_is_bit_identical_to_its_model(pqp, pH, nS, nI, B, K):
+    """Duals of the reference's MPC layout (constraint rows in +/- pairs) run on the PAIRED instantiation of the CTA-pair kernel:
+    only the N/2 representative rows go through the tensor cores, each epilogue thread updates a row and its partner.  The
+    handle's own tensor-core Qd has the structure element for element (checked on the device, and here with numpy); the kernel
+    equals tests/imma_model.py::run_paired bit for bit for N = 480, 272, 260 (two representatives in the second M tile), 512
+    (full tiles), 256 < N only, ragged batches; exploit_structure = 0 falls back to all N rows."""
+    prob, d, X = _mpc(11, pH, nS, nI, B)
+    with pqp.Solver(d, prob, batch_capacity=B) as s:
+        Y, _, _ = s.solve(X, iters=K, status=False)
+        Qd, th, _ = s.dual()
+        Fd, _ = s.linear_terms(B, want_fp=False)
+        assert has_pair_structure(Qd)
+        if d.N > 256:
+            assert s.last_kernel == "batched_imma_paired", s.last_kernel
+            n = min(B, 70)
+            assert np.array_equal(Y[:n], model_run_paired(Qd, th, Fd[:n], K), equal_nan=True)
+        else:
+            assert s.last_kernel == "batched_imma_pair", s.last_kernel
+    with pqp.Solver(d, prob, batch_capacity=B, exploit_structure=0) as s:
+        Y0, _, _ = s.solve(X, iters=K, status=False)
+        assert s.last_kernel == "batched_imma_pair", s.last_kernel
+        assert np.array_equal(Y0[:40], model_run(Qd, th, Fd[:40], K), equal_nan=True)
+    fin = np.isfinite(Y0).all(axis=1) & np.isfinite(Y).all(axis=1)
+    assert relerr(Y[fin], Y0[fin]) <= 1e-4          # the two schemes agree to rounding (each is held to the oracle elsewhere)
 
 
 @pytest.mark.parametrize("pH,nS,nI,B,K", [(30, 12, 4, 130, 150), (17, 4, 4, 97, 40), (9, 4, 4, 64, 30), (32, 4, 4, 33, 20)])
@@ -41,6 +70,7 @@ def test_single_cta_and_pair_kernels_are_bit_identical(pqp, monkeypatch, pH, nS,
     and the single-CTA kernel run the same arithmetic: same bits, for 2, 3 and 4 M tiles and ragged batches."""
     prob, d, X = _mpc(7, pH, nS, nI, B)
     out = {}
+    monkeypatch.setenv("PQP_IMMA_PAIRED", "0")     # all N rows in both kernels (the paired-rows scheme has its own test)
     for pair in ("0", "1"):
         monkeypatch.setenv("PQP_IMMA_PAIR", pair)
         with pqp.Solver(d, prob, batch_capacity=B) as s:
@@ -71,7 +101,7 @@ def test_c4_shape_against_oracle(pqp, oracle32, oracle64):
     K = 1000
     with pqp.Solver(d, prob, batch_capacity=200) as s:
         Y, U, st = s.solve(X, iters=K, primal=True)
-        assert s.last_kernel == "batched_imma_pair"
+        assert s.last_kernel == "batched_imma_paired"
         Qd, th, _ = s.dual()
         Fd, Fp = s.linear_terms(200)
     worst = 0.0
@@ -96,7 +126,7 @@ def test_c4_full_size_properties(pqp, oracle32):
     prob, d, X = _mpc(2024, 30, 12, 4, 4096)
     with pqp.Solver(d, prob, batch_capacity=4096) as s:
         Y, U, st = s.solve(X, iters=1000, primal=True)
-        assert s.last_kernel == "batched_imma_pair"
+        assert s.last_kernel == "batched_imma_paired"
         Fd, _ = s.linear_terms(4096, want_fp=False)
         Qd, _, _ = s.dual()
         Y2, _, st2 = s.solve(X, iters=1500)

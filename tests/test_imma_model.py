@@ -78,3 +78,48 @@ def test_model_degenerate_problems_follow_the_reference():
     assert np.all(Y == 0)
     Y = run(Qd, th, np.array([[-1.0, 2.0]], np.float32), 5, Y0=np.zeros((1, 2), np.float32))
     assert np.isnan(Y).all()
+
+
+def test_oracle_duals_of_the_mpc_layout_have_the_pair_structure(oracle32):
+    """Gp = [I; -I; C Gam; -C Gam] (the reference's N = 4*pHorizon*nInput layout; example/Gp.txt is [I; -I; 0; 0]): PQP_CPU.c's own
+    float Qd satisfies Qd[sigma(i)][j] == -Qd[i][j] == Qd[i][sigma(j)] element for element -- negating an operand row negates
+    every product and every partial sum exactly -- which is what the PAIRED tensor-core scheme relies on."""
+    from imma_model import has_pair_structure
+    Qd, th, Fd = _mpc_duals(oracle32, 3, 6, 5, 2, 1)
+    assert has_pair_structure(Qd)
+    g = np.load(__import__("os").path.join(__import__("conftest").GOLDEN, "golden_example.npz"))
+    assert has_pair_structure(g["Qd"])
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((8, 8)).astype(np.float32)
+    assert not has_pair_structure((A @ A.T).astype(np.float32))
+
+
+@pytest.mark.parametrize("pH,nS,nI,K", [(6, 5, 2, 60), (9, 4, 3, 120)])
+def test_paired_model_matches_oracle_and_the_plain_model(oracle32, oracle64, pH, nS, nI, K):
+    """The PAIRED arithmetic (half the products: only the representative rows are multiplied) against the oracle and its float64
+    twin with the tolerance rule of DESIGN.md 4, and next to the plain scheme: the two differ only in fp32 roundings of the
+    a_ii terms and in per-row scales, i.e. at the 1e-6 level."""
+    from imma_model import run_paired
+    B = 5
+    Qd, th, Fd = _mpc_duals(oracle32, 3, pH, nS, nI, B)
+    Yp = run_paired(Qd, th, Fd, K)
+    Y = run(Qd, th, Fd, K)
+    for b in range(B):
+        y32, _ = oracle32.solve_fixed(Qd, Fd[b], K)
+        y64, _ = oracle64.solve_fixed(Qd, Fd[b], K)
+        e_gf, e_gd, e_fd = relerr(Yp[b], y32), relerr(Yp[b], y64), relerr(y32, y64)
+        assert e_gf <= TOL or (e_gf <= 2 * e_fd and e_gd <= max(e_fd, TOL)), (b, e_gf, e_gd, e_fd)
+        assert np.array_equal(active_set(Yp[b], 1e-5), active_set(y32, 1e-5))
+        assert relerr(Yp[b], Y[b]) <= max(TOL, 2 * e_fd)
+
+
+def test_paired_model_c4_shape(oracle32, oracle64):
+    from imma_model import run_paired
+    Qd, th, Fd = _mpc_duals(oracle32, 2024, 30, 12, 4, 3)
+    K = 150
+    Y = run_paired(Qd, th, Fd, K)
+    for b in range(3):
+        y32, _ = oracle32.solve_fixed(Qd, Fd[b], K)
+        y64, _ = oracle64.solve_fixed(Qd, Fd[b], K)
+        assert relerr(Y[b], y64) <= max(2 * relerr(y32, y64), TOL)
+        assert np.array_equal(active_set(Y[b], 1e-5), active_set(y64, 1e-5))
