@@ -119,6 +119,12 @@ typedef struct pqp_opts {
 			       * tensor-core loop multiplies only the N/2 representative rows and updates each row together with its
 			       * partner: the same exact integer sums, half the work.  0: always all N rows.  Never applies to a Qd
 			       * without that structure */
+	int accelerate;    /* 0 (default): the reference's live loop, updateY2 only.  P > 0 with a fixed count: after every P-th
+			       * multiplicative update one acceleration / line-search step y <- y + alpha*ph, ph = max(0, -(Qd y + Fd)),
+			       * alpha = -((y'Qd + Fd')ph)/(ph'Qd ph) -- the branch solveQuadraticDual leaves dead behind `if(1)`
+			       * (PQP_CPU.c:721-735; computeph :625-630, computealphaY :545-575, updateY1 :579-588), with computeph's
+			       * `matrixAdd(ph, ph, ...)` read as `+= Fd` (as written it doubles Qd y and never sees Fd).  Not counted in
+			       * the update count, not applied after the last update; ignored when running to tolerance */
 } pqp_opts;
 
 /* Per-problem result of a solve (replaces the printf's of PQP_CPU.c:741,1005-1006). */

@@ -158,6 +158,22 @@ class Oracle(_Base):
         self._f("iterate")(_ptr(Y), _ptr(Qd), _ptr(Fd), C.c_int(Fd.size), C.c_long(K), self.real(theta_floor))
         return Y
 
+    def accel_step(self, Y, Qd, Fd):
+        """computeph + computealphaY + updateY1 (PQP_CPU.c:625-630, :545-588) with computeph's `+= ph` read as `+= Fd`;
+        returns (Y + alpha*ph, alpha)."""
+        Y, Qd, Fd = self.arr(Y), self.arr(Qd), self.arr(Fd)
+        Yn, alpha = self.zeros(Fd.size), self.zeros(1)
+        self._f("accel_step")(_ptr(Yn), _ptr(alpha), _ptr(Y), _ptr(Qd), _ptr(Fd), C.c_int(Fd.size))
+        return Yn, float(alpha[0])
+
+    def solve_accel(self, Qd, Fd, K, every, y_init=1000.0, theta_floor=5.0):
+        """K multiplicative updates with one acceleration step after every `every`-th of them (not after the last)."""
+        Qd, Fd = self.arr(Qd), self.arr(Fd)
+        Y = self.zeros(Fd.size)
+        self._f("solve_accel")(_ptr(Y), _ptr(Qd), _ptr(Fd), C.c_int(Fd.size), C.c_long(K), C.c_long(every), self.real(y_init),
+                               self.real(theta_floor))
+        return Y
+
     def solve_converge(self, Qd, Fd, Md, Qp, Qp_inv, Fp, Mp, Gp, Kp, y_init=1000.0, theta_floor=5.0,
                        max_h=10 ** 7, tol=None):
         """tol=None: the reference's 1e-6 (PQP_CPU.c:19-22); a number: the same test with erc = eac = eaj = erj = tol."""

@@ -52,7 +52,7 @@ class Opts(C.Structure):
     _fields_ = [("theta_floor", C.c_float), ("y_init", C.c_float), ("erc", C.c_float), ("eac", C.c_float),
                 ("eaj", C.c_float), ("erj", C.c_float), ("order", C.c_int), ("device", C.c_int),
                 ("max_iters", C.c_int), ("check_every", C.c_int), ("batch_capacity", C.c_int),
-                ("use_tensor_cores", C.c_int), ("l2_persist", C.c_int), ("exploit_symmetry", C.c_int), ("exploit_structure", C.c_int)]
+                ("use_tensor_cores", C.c_int), ("l2_persist", C.c_int), ("exploit_symmetry", C.c_int), ("exploit_structure", C.c_int), ("accelerate", C.c_int)]
 
 
 class Status(C.Structure):

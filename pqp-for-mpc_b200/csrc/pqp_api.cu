@@ -82,6 +82,11 @@ struct pqp_handle {
 	float *X, *Db, *Fp, *Fd, *Md, *Y, *U, *Tmp;
 	pqp_status *st;
 	int fp_B; /* problems whose Fp is cached from the last solve */
+	float *acc_ws;      /* [3][cap][N] scratch of the acceleration step (opts.accelerate), allocated on first use */
+	int acc_cap;
+	int iters_base;     /* updates applied by earlier chunks of the solve in progress (reported in pqp_status.iters) */
+	const float *cur_D; /* disturbance vectors of the solve being formed: h->D (stride 0) or h->Db (stride nDisH) */
+	int cur_Dstride;
 	/* single-problem loop state */
 	float *ybuf0, *ybuf1, *partials;
 	void *pk0, *pk1; /* {value, epoch} packet vectors of the flag-in-data y exchange */
@@ -125,6 +130,7 @@ void pqp_default_opts(pqp_opts *o)
 	o->l2_persist = 1;
 	o->exploit_symmetry = 1;
 	o->exploit_structure = 1;
+	o->accelerate = 0;
 }
 
 int pqp_output_offsets(const pqp_dims *d, const float *Z, const float *Theta, float *Kx, float *Kd)
@@ -566,7 +572,7 @@ void pqp_destroy(pqp_handle *h)
 		if (h->l2_limit_changed) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_limit_saved);
 	}
 	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
-			 h->Kx, h->Kd, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->imma_ptiles, h->imma_prowc, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
+			 h->Kx, h->Kd, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->imma_ptiles, h->imma_prowc, h->acc_ws, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
 			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf, h->pk0, h->pk1,
 			 h->sym.units, h->sym.cta_u0, h->sym.cta_j0, h->sym.strip_c0, h->sym.strip_c1, h->sym.rowpart, h->sym.colpart };
 	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
@@ -707,7 +713,7 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 			h->launches += iters;
 			done = iters;
 			if (want_status) {
-				CK(pqp_launch_status(st_dev, h->Q, ldq, N, bufs[done & 1], ldq, Fd, Md, h->Kp, h->o.erc, h->o.eac, 1, done, NULL, h->stream));
+				CK(pqp_launch_status(st_dev, h->Q, ldq, N, bufs[done & 1], ldq, Fd, Md, h->Kp, h->o.erc, h->o.eac, 1, done + h->iters_base, NULL, h->stream));
 				h->launches++;
 			}
 		} else {
@@ -885,8 +891,27 @@ static int ensure_batched_operands(pqp_handle *h)
 	return PQP_OK;
 }
 
-/* Fd already in h->Fd [B x N]; Md in h->Md when want_status */
-static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, pqp_status *st)
+enum { FUSE_REFRESH = 1, FUSE_RECOVER = 2 };
+
+/*
+ * Can this solve run as ONE launch of the paired-rows tensor-core kernel with the h(x) refresh (and the recovery) inside it?
+ * Needs: a batch, fixed count, FAST order, the int8 engine, a Qd with the +/- row-pair structure, the handle's own Fp model,
+ * no state-dependent constraint offsets (Kx / Kd: the separate kernels keep those), room for the scratch in the operand ring.
+ */
+static int fused_path(pqp_handle *h, int B, int iters)
+{
+	const char *e;
+	if (B <= 32 || iters <= 0 || h->o.order == PQP_ORDER_STRICT || !h->have_fp_model || h->Kx || h->Kd || h->o.accelerate > 0) return 0;
+	if ((e = pqp_env("PQP_IMMA_FUSE")) && atoi(e) == 0) return 0;
+	if ((e = pqp_env("PQP_IMMA_PAIR")) && atoi(e) == 0) return 0;
+	if (batched_engine(h) != BATCH_IMMA || !pqp_batched_imma_pair_supported(h->d.N)) return 0;
+	if (ensure_imma_paired(h) || h->paired_state != 1) return 0;
+	return pqp_batched_imma_paired_can_fuse(h->d.N, h->d.M, h->smem_optin);
+}
+
+/* Fd already in h->Fd [B x N]; Md in h->Md when want_status.  fuse (FUSE_*): the paired kernel forms Fp / Fd itself from h->X
+ * (form_linear_terms was told to skip them) and, with FUSE_RECOVER, leaves U in h->U. */
+static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, pqp_status *st, int fuse)
 {
 	const int N = h->d.N;
 	const int strict = h->o.order == PQP_ORDER_STRICT;
@@ -898,11 +923,39 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 	/* fixed count: any batched engine; run-to-tolerance (iters <= 0): the int8 engine evaluates the stop test per problem itself */
 	const int batched = B > 1 && !strict &&
 			    (iters > 0 ? (engine != BATCH_SIMT || pqp_batched_simt_supported(N)) : engine == BATCH_IMMA);
-	if (batched) {
+	if (fuse) {
+		/* one launch: refresh -> loop -> recovery (pqp_batched_imma_paired.cu) */
+		const int M = h->d.M;
+		if (Y0) CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+		pqp_paired_fuse fz;
+		memset(&fz, 0, sizeof fz);
+		fz.X = h->X; fz.D = h->cur_D; fz.D_stride = h->cur_Dstride; fz.nS = h->d.nState; fz.nd = h->d.nDisH; fz.M = M;
+		fz.Fp1 = h->Fp1; fz.Fp2 = h->Fp2; fz.Fp3 = h->Fp3; fz.Fp_const = h->Fp_const; fz.GQ = h->GQ; fz.Kp = h->Kp;
+		fz.Fp_out = h->Fp; fz.Fd_out = h->Fd;
+		if (fuse & FUSE_RECOVER) {
+			fz.Gp = h->Gp; fz.Qp_inv = h->Qp_inv; fz.Fp = h->Fp; fz.U = h->U;
+		}
+		fz.y0_const = Y0 == NULL;
+		fz.y_init = h->o.y_init;
+		CK(cudaEventRecord(h->ev0, h->stream));
+		CK(pqp_launch_batched_imma_paired(h->imma_ptiles, h->imma_prowc, N, B, h->Fd, h->Y, iters, h->smem_optin, &fz, h->stream));
+		CK(cudaEventRecord(h->ev1, h->stream));
+		h->ev_valid = 1;
+		h->launches++;
+		h->last_kernel = "batched_imma_paired";
+		h->fp_B = B;
+		if (want_status) {
+			/* Md needs the Fp the kernel formed: after it.  Jd = 1/2 y'Qd y + Fd'y + Md/2 (computeCost, PQP_CPU.c:648-666) */
+			CK(pqp_launch_md(h->Md, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, h->cur_D, h->cur_Dstride, h->X, B, M,
+					 h->d.nDisH, h->d.nState, h->stream));
+			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, h->Md, h->Kp, h->o.erc, h->o.eac, B, iters + h->iters_base, NULL, h->stream));
+			h->launches += 2;
+		}
+	} else if (batched) {
 		int rc = engine == BATCH_IMMA ? ensure_imma_tiles(h) : (engine == BATCH_UMMA ? ensure_umma_tiles(h) : ensure_batched_operands(h));
 		if (rc) return rc;
 		if (Y0) {
-			CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+			if (Y0 != h->Y) CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
 		} else {
 			CK(pqp_launch_fill(h->Y, h->o.y_init, (size_t)B * N, h->stream));
 			h->launches++;
@@ -925,7 +978,7 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 				int rc2 = ensure_imma_paired(h);
 				if (rc2) return rc2;
 				if (h->paired_state == 1) {
-					CK(pqp_launch_batched_imma_paired(h->imma_ptiles, h->imma_prowc, N, B, h->Fd, h->Y, iters, h->smem_optin, h->stream));
+					CK(pqp_launch_batched_imma_paired(h->imma_ptiles, h->imma_prowc, N, B, h->Fd, h->Y, iters, h->smem_optin, NULL, h->stream));
 					h->last_kernel = "batched_imma_paired";
 				} else {
 					CK(pqp_launch_batched_imma_pair(h->imma_tiles, h->imma_rowc, N, B, h->Fd, h->Y, iters, h->smem_optin, h->stream));
@@ -953,7 +1006,7 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 		h->ev_valid = 1;
 		h->launches++;
 		if (want_status && iters > 0) { /* in tolerance mode the kernel wrote the status of every problem itself */
-			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, Md, h->Kp, h->o.erc, h->o.eac, B, iters, NULL, h->stream));
+			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, Md, h->Kp, h->o.erc, h->o.eac, B, iters + h->iters_base, NULL, h->stream));
 			h->launches++;
 		}
 	} else {
@@ -978,7 +1031,45 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 	return PQP_OK;
 }
 
-static int form_linear_terms(pqp_handle *h, const float *X, const float *D, int B, int want_status)
+/*
+ * opts.accelerate = P > 0, fixed count: the K multiplicative updates run in chunks of P (each chunk on the loop kernel the plain
+ * solve would use) with one acceleration / line-search step between chunks (pqp_launch_accel_step; PQP_CPU.c:545-588, :625-630 --
+ * the branch the reference leaves dead behind `if(1)`, :721-735), not counted in K and not applied after the last update.
+ */
+static int run_loop_any(pqp_handle *h, int B, int iters, const float *Y0, float *Y, pqp_status *st, int fuse)
+{
+	const int P = h->o.accelerate;
+	h->iters_base = 0;
+	if (P <= 0 || iters <= 0 || iters <= P) return run_loop(h, B, iters, Y0, Y, st, fuse);
+	const int N = h->d.N;
+	if (h->acc_cap < h->cap) {
+		if (h->acc_ws) cudaFree(h->acc_ws);
+		h->acc_ws = NULL;
+		h->acc_cap = 0;
+		int rc = dalloc(&h->acc_ws, (size_t)3 * h->cap * N);
+		if (rc) return rc;
+		h->acc_cap = h->cap;
+	}
+	int done = 0;
+	const float *y0 = Y0;
+	while (done < iters) {
+		const int n = iters - done < P ? iters - done : P, last = done + n == iters;
+		h->iters_base = done;
+		int rc = run_loop(h, B, n, y0, last ? Y : NULL, last ? st : NULL, 0);
+		if (rc) return rc;
+		done += n;
+		y0 = h->Y;
+		if (!last) {
+			CK(pqp_launch_accel_step(h->Y, N, h->Q, h->ldq, h->Fd, h->acc_ws, B, N, h->stream));
+			h->launches += 4;
+		}
+	}
+	h->iters_base = 0;
+	return PQP_OK;
+}
+
+/* skip_fp_fd: the loop kernel forms Fp, Fd (and Md is launched behind it) -- only X and D are brought to the device here */
+static int form_linear_terms(pqp_handle *h, const float *X, const float *D, int B, int want_status, int skip_fp_fd)
 {
 	const int M = h->d.M, N = h->d.N, nS = h->d.nState, nd = h->d.nDisH;
 	const int strict = h->o.order == PQP_ORDER_STRICT;
@@ -992,6 +1083,9 @@ static int form_linear_terms(pqp_handle *h, const float *X, const float *D, int 
 		Dd = h->Db;
 		Dstride = nd;
 	}
+	h->cur_D = Dd;
+	h->cur_Dstride = Dstride;
+	if (skip_fp_fd) return PQP_OK;
 	CK(pqp_launch_fp(h->Fp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, Dd, Dstride, h->X, B, M, nd, nS, h->stream));
 	CK(pqp_launch_fd(h->Fd, h->GQ, h->Fp, h->Kp, B, N, M, strict, h->stream));
 	h->launches += 2;
@@ -1016,8 +1110,9 @@ int pqp_solve_batch(pqp_handle *h, const float *X, const float *D, int B, int it
 	CK(cudaSetDevice(h->device));
 	int rc = ensure_capacity(h, B);
 	if (rc) return rc;
-	if ((rc = form_linear_terms(h, X, D, B, st != NULL || iters <= 0))) return rc;
-	if ((rc = run_loop(h, B, iters, Y0, Y, st))) return rc;
+	const int fuse = fused_path(h, B, iters) ? FUSE_REFRESH : 0;
+	if ((rc = form_linear_terms(h, X, D, B, st != NULL || iters <= 0, fuse))) return rc;
+	if ((rc = run_loop_any(h, B, iters, Y0, Y, st, fuse))) return rc;
 	CK(cudaStreamSynchronize(h->stream));
 	return PQP_OK;
 }
@@ -1034,7 +1129,7 @@ int pqp_solve_dual_full(pqp_handle *h, const float *Fd, const float *Md, int B, 
 	h->fp_B = 0;
 	const int saved = h->have_fp_model;
 	h->have_fp_model = Md != NULL; /* without Md, Jd is reported (and tested) without the constant Md/2 */
-	rc = run_loop(h, B, iters, Y0, Y, st);
+	rc = run_loop_any(h, B, iters, Y0, Y, st, 0);
 	h->have_fp_model = saved;
 	if (rc) return rc;
 	CK(cudaStreamSynchronize(h->stream));
@@ -1106,9 +1201,11 @@ int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B,
 	CK(cudaSetDevice(h->device));
 	int rc = ensure_capacity(h, B);
 	if (rc) return rc;
-	if ((rc = form_linear_terms(h, X, D, B, st != NULL || iters <= 0))) return rc;
-	if ((rc = run_loop(h, B, iters, Y0, Y, st))) return rc;
-	if ((rc = recover_on_device(h, h->Y, h->d.N, NULL, B, U))) return rc;
+	const int fuse = (h->have_primal && h->d.M > 0 && fused_path(h, B, iters)) ? (FUSE_REFRESH | FUSE_RECOVER) : 0;
+	if ((rc = form_linear_terms(h, X, D, B, st != NULL || iters <= 0, fuse))) return rc;
+	if ((rc = run_loop_any(h, B, iters, Y0, Y, st, fuse))) return rc;
+	if (fuse) CK(cudaMemcpyAsync(U, h->U, (size_t)B * h->d.M * sizeof(float), cudaMemcpyDefault, h->stream)); /* the kernel's epilogue left U in h->U */
+	else if ((rc = recover_on_device(h, h->Y, h->d.N, NULL, B, U))) return rc;
 	CK(cudaStreamSynchronize(h->stream));
 	return PQP_OK;
 }

@@ -292,6 +292,18 @@ struct BiParams {
 	const float *Kp;             /* [N] or NULL */
 	const float *Md;             /* [B] or NULL */
 	pqp_status *status;          /* [B], written in tolerance mode */
+	/* pqp_batched_imma_paired.cu only -- the h(x) refresh and the primal recovery inside the loop kernel (0 / NULL: not fused):
+	 *   fx_GQ != NULL: Fp_b = Fp1 D_b + Fp2 x_b - Fp3 (computeFp, PQP_CPU.c:373-382) and Fd_b = GQ Fp_b + Kp (computeFd, :456-460) are
+	 *   formed by the kernel's prologue in the reference's order and also written to fx_Fp_out / fx_Fd_out; Fd (above) is not read.
+	 *   rc_U != NULL: U_b = -Qp_inv (Gp' y_b + Fp_b) (computeUfromY, :352-360) by the kernel's epilogue, reference order.
+	 *   y0_const: Y holds no start vector, every dual starts at y_init (PQP_CPU.c:710). */
+	const float *fx_X, *fx_D, *fx_Fp1, *fx_Fp2, *fx_Fp3, *fx_Fpc, *fx_GQ, *fx_Kp;
+	int fx_nS, fx_nd, fx_Dstride, fx_M;
+	float *fx_Fp_out, *fx_Fd_out;
+	const float *rc_Gp, *rc_Qp_inv, *rc_Fp;
+	float *rc_U;
+	int y0_const;
+	float y_init;
 	int dbg;                     /* experiment switches (PQP_IMMA_DBG): 2 skip all MMAs, 4 skip epilogue math, 8 print wait-time profile */
 	long long *prof;             /* dbg & 8: [8] cycle counters of CTA 0 (see PROF_*) */
 };

@@ -68,6 +68,9 @@ cudaError_t pqp_launch_update_y2_dense(float *Yn, const float *Y, const float *Q
  * reference order and promotions; tmp [n] scratch; all device pointers */
 cudaError_t pqp_launch_quad_form(float *out, float *tmp, const float *z, const float *A, const float *F, const float *m, int n, int mode,
 				 cudaStream_t s);
+/* one acceleration / line-search step on B duals in place (computeph + computealphaY + updateY1, PQP_CPU.c:625-630, :545-588, with
+ * computeph's self-addition read as += Fd): y += alpha*max(0, -(Qd y + Fd)); reference order; ws [3][B][N] scratch; 4 launches */
+cudaError_t pqp_launch_accel_step(float *Y, int ldy, const float *Q, int ldq, const float *Fd, float *ws, int B, int N, cudaStream_t s);
 /* fill n floats */
 cudaError_t pqp_launch_fill(float *p, float v, size_t n, cudaStream_t s);
 
@@ -174,8 +177,23 @@ size_t pqp_batched_imma_paired_tiles_bytes(int N);
 size_t pqp_batched_imma_paired_rowc_bytes(int N);
 cudaError_t pqp_launch_pair_struct_check(const float *Q, int ldq, int N, unsigned *bad, cudaStream_t s);
 cudaError_t pqp_launch_build_imma_tiles_paired(void *tiles, void *rowc, const float *Q, int ldq, const float *theta, int N, cudaStream_t s);
+/* the per-solve small steps inside that kernel (north star: "fused into the same kernel ... fused epilogue"):
+ *   GQ != NULL  prologue: Fp_b = Fp1 D_b + Fp2 x_b - Fp3 (computeFp) and Fd_b = GQ Fp_b + Kp (computeFd), reference order, also
+ *               written to Fp_out [B x M] / Fd_out [B x N]; the launcher's Fd argument is then not read
+ *   U != NULL   epilogue: U_b = -Qp_inv (Gp' y_b + Fp_b) (computeUfromY), reference order; Fp [B x M] (= Fp_out when both are fused)
+ *   y0_const    every dual starts at y_init; Y is output only */
+typedef struct pqp_paired_fuse {
+	const float *X, *D, *Fp1, *Fp2, *Fp3, *Fp_const, *GQ, *Kp;
+	int nS, nd, D_stride, M;
+	float *Fp_out, *Fd_out;
+	const float *Gp, *Qp_inv, *Fp;
+	float *U;
+	int y0_const;
+	float y_init;
+} pqp_paired_fuse;
+int pqp_batched_imma_paired_can_fuse(int N, int M, size_t smem_optin);
 cudaError_t pqp_launch_batched_imma_paired(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters,
-					   size_t smem_optin, cudaStream_t s);
+					   size_t smem_optin, const pqp_paired_fuse *fz, cudaStream_t s);
 #define PQP_BATCH_KPAD 16
 #define PQP_BATCH_IPAD 128
 

@@ -579,3 +579,92 @@ cudaError_t pqp_launch_quad_form(float *out, float *tmp, const float *z, const f
 	quad_finish_kernel<<<1, 32, 0, s>>>(out, tmp, z, F, m, n, mode);
 	return cudaGetLastError();
 }
+
+/* ---- Brand's acceleration / line-search step (the dead branch of PQP_CPU.c:721-735: computeph :625-630, computealphaY :545-575,
+ * updateY1 :579-588; computeph's `matrixAdd(ph, ph, ...)` read as `+= Fd`, the evident fix) -- opt-in, pqp_opts.accelerate ----
+ *     ph = max(0, -(Qd y + Fd));   alpha = -((y'Qd + Fd') ph) / (ph'Qd ph) if ph'Qd ph > 0 else 0;   y <- y + alpha ph
+ * Every sum in matrixMultiply's order (k ascending from zero, separately rounded multiply and add), so the step is bit-identical to
+ * the oracle's restatement in both orders of the library.  Three passes over Qd per step (row form for ph, column form for
+ * ph'Qd and y'Qd, as the reference multiplies them), each as the tiled sequential-k product of fd_seq_kernel.
+ *   seqdot_kernel<COL, EPI>: out[b][i] = epi(sum_k A(i,k) V[b][k]),  A(i,k) = Q[i][k] (COL = 0) or Q[k][i] (COL = 1)
+ *   EPI 0: the sum;  1: sum + 1*Fd[b][i];  2: max(0, -(sum + 1*Fd[b][i])) */
+template <int COL, int EPI>
+__global__ void __launch_bounds__(256) seqdot_kernel(float *__restrict__ out, const float *__restrict__ Q, int ldq, const float *__restrict__ V, int ldv,
+						      const float *__restrict__ Fd, int B, int N)
+{
+	__shared__ float a_s[32][65], v_s[32][65];
+	const int i0 = blockIdx.x * 32, b0 = blockIdx.y * 32;
+	const int tid = threadIdx.x, r = tid % 32, pg = tid / 32; /* thread = (row r, problems pg, pg+8, pg+16, pg+24) */
+	float acc[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+	for (int k0 = 0; k0 < N; k0 += 64) {
+		const int kc = min(64, N - k0);
+		for (int e = tid; e < 32 * 64; e += 256) {
+			if (COL) { /* A(i,k) = Q[k][i]: consecutive threads along i */
+				const int kk = e / 32, rr = e % 32;
+				a_s[rr][kk] = (i0 + rr < N && kk < kc) ? Q[(size_t)(k0 + kk) * ldq + i0 + rr] : 0.0f;
+			} else {
+				const int rr = e / 64, kk = e % 64;
+				a_s[rr][kk] = (i0 + rr < N && kk < kc) ? Q[(size_t)(i0 + rr) * ldq + k0 + kk] : 0.0f;
+			}
+			const int rb = e / 64, kb = e % 64;
+			v_s[rb][kb] = (b0 + rb < B && kb < kc) ? V[(size_t)(b0 + rb) * ldv + k0 + kb] : 0.0f;
+		}
+		__syncthreads();
+		for (int k = 0; k < kc; k++) {
+			const float a = a_s[r][k];
+#pragma unroll
+			for (int u = 0; u < 4; u++) acc[u] = __fadd_rn(acc[u], __fmul_rn(a, v_s[pg + 8 * u][k]));
+		}
+		__syncthreads();
+	}
+	if (i0 + r < N) {
+#pragma unroll
+		for (int u = 0; u < 4; u++) {
+			const int b = b0 + pg + 8 * u;
+			if (b >= B) continue;
+			float v = acc[u];
+			if (EPI >= 1) v = __fadd_rn(v, __fmul_rn(1.0f, Fd[(size_t)b * N + i0 + r]));
+			if (EPI == 2) v = (0.0f > -v) ? 0.0f : -v;
+			out[(size_t)b * N + i0 + r] = v;
+		}
+	}
+}
+
+/* one block per problem: thread 0 walks the two dot products in order, then the block applies y += alpha*ph */
+__global__ void __launch_bounds__(256) accel_finish_kernel(float *__restrict__ Y, int ldy, const float *__restrict__ ph, const float *__restrict__ t,
+							    const float *__restrict__ t2, int N)
+{
+	__shared__ float alpha_s;
+	const int b = blockIdx.x;
+	const float *p = ph + (size_t)b * N, *tt = t + (size_t)b * N, *tt2 = t2 + (size_t)b * N;
+	if (threadIdx.x == 0) {
+		float s0 = 0.0f, alpha = 0.0f;
+		for (int j = 0; j < N; j++) s0 = __fadd_rn(s0, __fmul_rn(tt[j], p[j]));
+		if (s0 > 0.0f) {
+			float s2 = 0.0f;
+			for (int j = 0; j < N; j++) s2 = __fadd_rn(s2, __fmul_rn(tt2[j], p[j]));
+			alpha = __fdiv_rn(-s2, s0);
+		}
+		alpha_s = alpha;
+	}
+	__syncthreads();
+	const float alpha = alpha_s;
+	float *y = Y + (size_t)b * ldy;
+	for (int i = threadIdx.x; i < N; i += blockDim.x) y[i] = __fadd_rn(y[i], __fmul_rn(alpha, p[i]));
+}
+
+/* ws: [3][B][N] scratch (ph, ph'Qd, y'Qd + Fd') */
+cudaError_t pqp_launch_accel_step(float *Y, int ldy, const float *Q, int ldq, const float *Fd, float *ws, int B, int N, cudaStream_t s)
+{
+	float *ph = ws, *t = ws + (size_t)B * N, *t2 = t + (size_t)B * N;
+	for (int b0 = 0; b0 < B; b0 += 32 * 65535) { /* gridDim.y limit */
+		const int nb = min(B - b0, 32 * 65535);
+		const dim3 grid((N + 31) / 32, (nb + 31) / 32);
+		const size_t o = (size_t)b0 * N;
+		seqdot_kernel<0, 2><<<grid, 256, 0, s>>>(ph + o, Q, ldq, Y + (size_t)b0 * ldy, ldy, Fd + o, nb, N);
+		seqdot_kernel<1, 0><<<grid, 256, 0, s>>>(t + o, Q, ldq, ph + o, N, NULL, nb, N);
+		seqdot_kernel<1, 1><<<grid, 256, 0, s>>>(t2 + o, Q, ldq, Y + (size_t)b0 * ldy, ldy, Fd + o, nb, N);
+	}
+	accel_finish_kernel<<<B, 256, 0, s>>>(Y, ldy, ph, t, t2, N);
+	return cudaGetLastError();
+}

@@ -260,3 +260,44 @@ def test_stopping_points_against_the_reference_stop_test(pqp, oracle32):
     assert 0.9 <= np.median(ratio) <= 1.1 and ratio.min() >= 0.7 and ratio.max() <= 1.5
     for b in range(n):
         assert np.abs(U[b] - ref[b][1]).max() <= 2e-4 * max(np.abs(ref[b][1]).max(), 1.0), b
+
+
+@pytest.mark.parametrize("pH,nS,nI,B", [(30, 12, 4, 200), (17, 4, 4, 97), (32, 4, 4, 65)])
+def test_refresh_and_recovery_fused_into_the_loop_kernel(pqp, oracle32, monkeypatch, pH, nS, nI, B):
+    """pqp_solve_batch_primal on the paired-rows kernel is ONE launch: computeFp + computeFd (PQP_CPU.c:373-382, :456-460) in its
+    prologue, computeUfromY (:352-360) in its epilogue, all in the reference's order -- bit-identical to the separate
+    fp / fd / recover kernels (PQP_IMMA_FUSE=0), Fd and Fp bit-identical to the oracle's, U bit-identical to the oracle's
+    computeUfromY on the GPU's y; warm starts (Y0) and per-problem disturbances (D) included."""
+    prob, d, X = _mpc(5, pH, nS, nI, B)
+    rng = np.random.default_rng(1)
+    Dm = (prob["D"][None, :] + 0.05 * rng.standard_normal((B, d.nDisH))).astype(np.float32)
+    K = 40
+    out = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("PQP_IMMA_FUSE", fuse)
+        with pqp.Solver(d, prob, batch_capacity=B) as s:
+            s.solve(X, iters=1, primal=True, status=False)           # the one-time launches (structure test, digit planes) happen here
+            l0 = s.launch_count
+            Y, U, _ = s.solve(X, iters=K, primal=True, status=False)
+            n1 = s.launch_count - l0
+            assert s.last_kernel == "batched_imma_paired"
+            Fd, Fp = s.linear_terms(B)
+            Y2, U2, st2 = s.solve(X, iters=K, primal=True, D=Dm, Y0=Y)        # warm start, per-problem D, status
+            Fd2, Fp2 = s.linear_terms(B)
+            out[fuse] = (Y, U, Fd, Fp, Y2, U2, Fd2, Fp2, st2, n1)
+    f, u = out["1"], out["0"]
+    assert f[9] == 1 and u[9] >= 6, (f[9], u[9])          # one launch against fp, fd, fill, loop, recover x 2
+    for a, b in zip(f[:8], u[:8]):
+        assert np.array_equal(a, b, equal_nan=True)
+    for k in ("iters", "min_slack", "gap", "Jd", "kkt"):
+        assert np.array_equal(f[8][k], u[8][k], equal_nan=True), k
+    for b in (0, B // 2, B - 1):
+        Fpb = oracle32.compute_fp(prob["Fp1"], prob["Fp2"], prob["Fp3"], prob["D"], X[b])
+        _, Fdb, _, _ = oracle32.convert_to_dual(prob["Qp_inv"], prob["Gp"], prob["Kp"], Fpb, 0.0, want_qd=False)
+        assert np.array_equal(f[3][b], Fpb)
+        # Fd = GQ Fp + Kp (a cancelling sum) with the handle's tensor-core GQ: against the oracle's reference-order GQ only to rounding
+        assert relerr(f[2][b], Fdb) <= 2e-5
+        if np.isfinite(f[0][b]).all():
+            assert np.array_equal(f[1][b], oracle32.recover_u(f[0][b], Fpb, prob["Gp"], prob["Qp_inv"]))
+        Fpd = oracle32.compute_fp(prob["Fp1"], prob["Fp2"], prob["Fp3"], Dm[b], X[b])
+        assert np.array_equal(f[7][b], Fpd)
