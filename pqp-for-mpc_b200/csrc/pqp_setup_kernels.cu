@@ -584,7 +584,7 @@ cudaError_t pqp_launch_quad_form(float *out, float *tmp, const float *z, const f
  * updateY1 :579-588; computeph's `matrixAdd(ph, ph, ...)` read as `+= Fd`, the evident fix) -- opt-in, pqp_opts.accelerate ----
  *     ph = max(0, -(Qd y + Fd));   alpha = -((y'Qd + Fd') ph) / (ph'Qd ph) if ph'Qd ph > 0 else 0;   y <- y + alpha ph
  * Every sum in matrixMultiply's order (k ascending from zero, separately rounded multiply and add), so the step is bit-identical to
- * the oracle's restatement in both orders of the library.  Three passes over Qd per step (row form for ph, column form for
+ * the reference's arithmetic (with that fix) in both orders of the library.  Three passes over Qd per step (row form for ph, column form for
  * ph'Qd and y'Qd, as the reference multiplies them), each as the tiled sequential-k product of fd_seq_kernel.
  *   seqdot_kernel<COL, EPI>: out[b][i] = epi(sum_k A(i,k) V[b][k]),  A(i,k) = Q[i][k] (COL = 0) or Q[k][i] (COL = 1)
  *   EPI 0: the sum;  1: sum + 1*Fd[b][i];  2: max(0, -(sum + 1*Fd[b][i])) */
