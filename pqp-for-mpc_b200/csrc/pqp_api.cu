@@ -82,6 +82,9 @@ struct pqp_handle {
 	float *X, *Db, *Fp, *Fd, *Md, *Y, *U, *Tmp;
 	pqp_status *st;
 	int fp_B; /* problems whose Fp is cached from the last solve */
+	float *tol_ws;      /* run-to-tolerance on the paired kernel: evaluation partials | resume maxima [cap] | kept duals [cap x N] */
+	unsigned *tol_flags; /* frozen [cap] | newly [cap] | remaining [1] */
+	int tol_cap;
 	float *acc_ws;      /* [3][cap][N] scratch of the acceleration step (opts.accelerate), allocated on first use */
 	int acc_cap;
 	int iters_base;     /* updates applied by earlier chunks of the solve in progress (reported in pqp_status.iters) */
@@ -572,7 +575,7 @@ void pqp_destroy(pqp_handle *h)
 		if (h->l2_limit_changed) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_limit_saved);
 	}
 	void *ptrs[] = { h->Q, h->QT, h->theta, h->GQ, h->Gp, h->Qp_inv, h->Kp, h->Fp1, h->Fp2, h->Fp3, h->Fp_const, h->D,
-			 h->Kx, h->Kd, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->imma_ptiles, h->imma_prowc, h->acc_ws, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
+			 h->Kx, h->Kd, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->QpT, h->QnT, h->umma_tiles, h->imma_tiles, h->imma_rowc, h->imma_ptiles, h->imma_prowc, h->acc_ws, h->tol_ws, h->tol_flags, h->X, h->Db, h->Fp, h->Fd, h->Md, h->Y,
 			 h->U, h->Tmp, h->st, h->ybuf0, h->ybuf1, h->partials, h->barrier, h->result_buf, h->pk0, h->pk1,
 			 h->sym.units, h->sym.cta_u0, h->sym.cta_j0, h->sym.strip_c0, h->sym.strip_c1, h->sym.rowpart, h->sym.colpart };
 	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
@@ -901,12 +904,87 @@ enum { FUSE_REFRESH = 1, FUSE_RECOVER = 2 };
 static int fused_path(pqp_handle *h, int B, int iters)
 {
 	const char *e;
-	if (B <= 32 || iters <= 0 || h->o.order == PQP_ORDER_STRICT || !h->have_fp_model || h->Kx || h->Kd || h->o.accelerate > 0) return 0;
+	if (B <= 32 || h->o.order == PQP_ORDER_STRICT || !h->have_fp_model || h->Kx || h->Kd || (iters > 0 && h->o.accelerate > 0)) return 0;
+	if (iters <= 0 && pqp_env("PQP_IMMA_PAIRED_TOL") && atoi(pqp_env("PQP_IMMA_PAIRED_TOL")) == 0) return 0;
 	if ((e = pqp_env("PQP_IMMA_FUSE")) && atoi(e) == 0) return 0;
 	if ((e = pqp_env("PQP_IMMA_PAIR")) && atoi(e) == 0) return 0;
 	if (batched_engine(h) != BATCH_IMMA || !pqp_batched_imma_pair_supported(h->d.N)) return 0;
 	if (ensure_imma_paired(h) || h->paired_state != 1) return 0;
 	return pqp_batched_imma_paired_can_fuse(h->d.N, h->d.M, h->smem_optin);
+}
+
+/*
+ * Run to tolerance (iters <= 0) on the paired-rows kernel: chunks of check_every updates followed by ONE evaluation pass inside the
+ * same launch (g = Qd y + Fd from the sums the loop forms anyway), a tiny decide kernel that applies terminate()'s test per problem
+ * (PQP_CPU.c:673-687) and keeps the duals of every problem that passes exactly as they stand, one 4-byte read-back of "how many are
+ * still running" per chunk.  The next chunk resumes from the device-resident duals with the scale state the uninterrupted loop would
+ * have (m_resume), so a problem's result equals the fixed-count solve at its own count bit for bit (tested).  Problems that have
+ * passed keep being multiplied along with their batch mates (their kept result is not touched).
+ */
+static int tol_chunked(pqp_handle *h, int B, const float *Y0, float *Y, pqp_status *st, int fuse_refresh, const float *Md)
+{
+	const int N = h->d.N, M = h->d.M;
+	if (h->tol_cap < h->cap) {
+		if (h->tol_ws) cudaFree(h->tol_ws);
+		if (h->tol_flags) cudaFree(h->tol_flags);
+		h->tol_ws = NULL;
+		h->tol_flags = NULL;
+		h->tol_cap = 0;
+		int rc;
+		if ((rc = dalloc(&h->tol_ws, pqp_paired_eval_part_floats(h->cap) + (size_t)h->cap + (size_t)h->cap * N)) ||
+		    (rc = dalloc(&h->tol_flags, (size_t)2 * h->cap + 1)))
+			return rc;
+		h->tol_cap = h->cap;
+	}
+	float *part = h->tol_ws, *mres = part + pqp_paired_eval_part_floats(h->cap), *Yres = mres + h->cap;
+	unsigned *frozen = h->tol_flags, *newly = frozen + h->cap, *remaining = newly + h->cap;
+	CK(cudaMemsetAsync(frozen, 0, (size_t)B * sizeof(unsigned), h->stream));
+	if (Y0) CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+	const int every = h->o.check_every > 0 ? h->o.check_every : 1, cap_it = h->o.max_iters > 0 ? h->o.max_iters : 1;
+	int count = 0, first = 1;
+	CK(cudaEventRecord(h->ev0, h->stream));
+	for (;;) {
+		const int n = cap_it - count < every ? cap_it - count : every;
+		pqp_paired_fuse fz;
+		memset(&fz, 0, sizeof fz);
+		fz.M = M;
+		if (first && fuse_refresh) {
+			fz.X = h->X; fz.D = h->cur_D; fz.D_stride = h->cur_Dstride; fz.nS = h->d.nState; fz.nd = h->d.nDisH;
+			fz.Fp1 = h->Fp1; fz.Fp2 = h->Fp2; fz.Fp3 = h->Fp3; fz.Fp_const = h->Fp_const; fz.GQ = h->GQ; fz.Kp = h->Kp;
+			fz.Fp_out = h->Fp; fz.Fd_out = h->Fd;
+		}
+		fz.y0_const = first && Y0 == NULL;
+		fz.y_init = h->o.y_init;
+		fz.m_resume = first ? NULL : mres;
+		fz.m_out = mres;
+		fz.eval_part = part;
+		fz.tol_Kp = h->Kp; fz.erc = h->o.erc; fz.eac = h->o.eac;
+		CK(pqp_launch_batched_imma_paired(h->imma_ptiles, h->imma_prowc, N, B, h->Fd, h->Y, n, h->smem_optin, &fz, h->stream));
+		h->launches++;
+		count += n;
+		if (first && fuse_refresh) {
+			h->fp_B = B;
+			if (Md) { /* Md needs the Fp the kernel formed */
+				CK(pqp_launch_md(h->Md, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, h->cur_D, h->cur_Dstride, h->X, B, M,
+						 h->d.nDisH, h->d.nState, h->stream));
+				h->launches++;
+			}
+		}
+		CK(pqp_launch_paired_tol_decide(part, Md, h->st, frozen, newly, remaining, Yres, h->Y, B, N, count, cap_it, h->o.eaj, h->o.erj, h->stream));
+		h->launches += 2;
+		unsigned rem = 0;
+		CK(cudaMemcpyAsync(&rem, remaining, sizeof rem, cudaMemcpyDeviceToHost, h->stream));
+		CK(cudaStreamSynchronize(h->stream));
+		first = 0;
+		if (rem == 0) break;
+	}
+	CK(cudaEventRecord(h->ev1, h->stream));
+	h->ev_valid = 1;
+	h->last_kernel = "batched_imma_paired_tol";
+	CK(cudaMemcpyAsync(h->Y, Yres, (size_t)B * N * sizeof(float), cudaMemcpyDeviceToDevice, h->stream)); /* the kept duals are the result */
+	if (Y) CK(cudaMemcpyAsync(Y, h->Y, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+	if (st) CK(cudaMemcpyAsync(st, h->st, (size_t)B * sizeof(pqp_status), cudaMemcpyDefault, h->stream));
+	return PQP_OK;
 }
 
 /* Fd already in h->Fd [B x N]; Md in h->Md when want_status.  fuse (FUSE_*): the paired kernel forms Fp / Fd itself from h->X
@@ -923,6 +1001,12 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 	/* fixed count: any batched engine; run-to-tolerance (iters <= 0): the int8 engine evaluates the stop test per problem itself */
 	const int batched = B > 1 && !strict &&
 			    (iters > 0 ? (engine != BATCH_SIMT || pqp_batched_simt_supported(N)) : engine == BATCH_IMMA);
+	if (iters <= 0 && B > 32 && !strict && engine == BATCH_IMMA && pqp_batched_imma_pair_supported(N) &&
+	    !(pqp_env("PQP_IMMA_PAIR") && atoi(pqp_env("PQP_IMMA_PAIR")) == 0) && !(pqp_env("PQP_IMMA_PAIRED_TOL") && atoi(pqp_env("PQP_IMMA_PAIRED_TOL")) == 0)) {
+		int rc = ensure_imma_paired(h);
+		if (rc) return rc;
+		if (h->paired_state == 1) return tol_chunked(h, B, Y0, Y, st, fuse & FUSE_REFRESH, Md);
+	}
 	if (fuse) {
 		/* one launch: refresh -> loop -> recovery (pqp_batched_imma_paired.cu) */
 		const int M = h->d.M;
@@ -1201,10 +1285,10 @@ int pqp_solve_batch_primal(pqp_handle *h, const float *X, const float *D, int B,
 	CK(cudaSetDevice(h->device));
 	int rc = ensure_capacity(h, B);
 	if (rc) return rc;
-	const int fuse = (h->have_primal && h->d.M > 0 && fused_path(h, B, iters)) ? (FUSE_REFRESH | FUSE_RECOVER) : 0;
+	const int fuse = (h->have_primal && h->d.M > 0 && fused_path(h, B, iters)) ? (iters > 0 ? (FUSE_REFRESH | FUSE_RECOVER) : FUSE_REFRESH) : 0;
 	if ((rc = form_linear_terms(h, X, D, B, st != NULL || iters <= 0, fuse))) return rc;
 	if ((rc = run_loop_any(h, B, iters, Y0, Y, st, fuse))) return rc;
-	if (fuse) CK(cudaMemcpyAsync(U, h->U, (size_t)B * h->d.M * sizeof(float), cudaMemcpyDefault, h->stream)); /* the kernel's epilogue left U in h->U */
+	if (fuse & FUSE_RECOVER) CK(cudaMemcpyAsync(U, h->U, (size_t)B * h->d.M * sizeof(float), cudaMemcpyDefault, h->stream)); /* the kernel's epilogue left U in h->U */
 	else if ((rc = recover_on_device(h, h->Y, h->d.N, NULL, B, U))) return rc;
 	CK(cudaStreamSynchronize(h->stream));
 	return PQP_OK;

@@ -304,6 +304,15 @@ struct BiParams {
 	float *rc_U;
 	int y0_const;
 	float y_init;
+	/* pqp_batched_imma_paired.cu only -- run to tolerance in chunks (the host drives; pqp_api.cu tol_chunked):
+	 *   m_resume [B]: max_k y[k] of the iterate BEFORE the start vector (left in m_out by the previous chunk): the start digits are then
+	 *   quantised with the bound-based scale the uninterrupted loop would have used, so a chunked run equals the one-shot run bit for bit;
+	 *   eval_part != NULL: after the `iters` updates one EVALUATION pass (same MMAs, no update) forms g = den - num = Qd y + Fd per row and
+	 *   leaves, per warp and problem, {max(-g - tol), min g, sum y g, sum y (g + Fd)/2, max |min(y, g)|} in eval_part
+	 *   [pair][rank][warp][group][8][5] -- the terms of terminate() (PQP_CPU.c:673-687), folded in a fixed order */
+	const float *m_resume;
+	float *m_out;
+	float *eval_part;
 	int dbg;                     /* experiment switches (PQP_IMMA_DBG): 2 skip all MMAs, 4 skip epilogue math, 8 print wait-time profile */
 	long long *prof;             /* dbg & 8: [8] cycle counters of CTA 0 (see PROF_*) */
 };

@@ -190,7 +190,15 @@ typedef struct pqp_paired_fuse {
 	float *U;
 	int y0_const;
 	float y_init;
+	/* run to tolerance in chunks: resume state in / out, evaluation partials out (NULL: a plain fixed-count launch), compare()'s tolerances */
+	const float *m_resume;
+	float *m_out, *eval_part;
+	const float *tol_Kp;
+	float erc, eac;
 } pqp_paired_fuse;
+size_t pqp_paired_eval_part_floats(int B);
+cudaError_t pqp_launch_paired_tol_decide(const float *part, const float *Md, pqp_status *st, unsigned *frozen, unsigned *newly, unsigned *remaining,
+					 float *Yres, const float *Y, int B, int N, int count, int max_iters, float eaj, float erj, cudaStream_t s);
 int pqp_batched_imma_paired_can_fuse(int N, int M, size_t smem_optin);
 cudaError_t pqp_launch_batched_imma_paired(const void *tiles, const void *rowc, int N, int B, const float *Fd, float *Y, int iters,
 					   size_t smem_optin, const pqp_paired_fuse *fz, cudaStream_t s);

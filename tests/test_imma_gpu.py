@@ -301,3 +301,37 @@ def test_refresh_and_recovery_fused_into_the_loop_kernel(pqp, oracle32, monkeypa
             assert np.array_equal(f[1][b], oracle32.recover_u(f[0][b], Fpb, prob["Gp"], prob["Qp_inv"]))
         Fpd = oracle32.compute_fp(prob["Fp1"], prob["Fp2"], prob["Fp3"], Dm[b], X[b])
         assert np.array_equal(f[7][b], Fpd)
+
+
+def test_run_to_tolerance_on_the_paired_rows_kernel(pqp, monkeypatch):
+    """iters <= 0 on the paired-rows kernel (N > 256, MPC layout): chunks of check_every updates + an evaluation pass in the same
+    launch, terminate()'s test per problem in a decide kernel, the duals of a problem that passes kept exactly as they stand.
+    Properties: every problem's result is bit-identical to the fixed-count solve at its own count (the chunks resume with the
+    scale state of the uninterrupted loop); the status block is the one of that y; the single-CTA tolerance kernel (all N rows,
+    exact-maximum scales) stops within one check of the same counts at the same solution; U comes from the kept duals."""
+    prob, d, X = _mpc(2024, 30, 12, 4, 100)
+    X = (X * 0.5).astype(np.float32)                      # x_scale 30: every state converges within a few thousand updates
+    opts = dict(batch_capacity=100, eaj=1e-2, erj=1e-6, check_every=16, max_iters=8000)
+    with pqp.Solver(d, prob, **opts) as s:
+        Y, U, st = s.solve(X, iters=0, primal=True)
+        assert s.last_kernel == "batched_imma_paired_tol", s.last_kernel
+        fin = np.isfinite(Y).all(axis=1)
+        assert st["converged"][fin].mean() > 0.9 and np.all(st["iters"] % 16 == 0) and st["iters"].min() >= 16
+        conv = st["converged"] == 1
+        assert np.all(np.abs(st["gap"][conv]) <= 1e-2)
+        for b in (0, 41, 99):
+            k = int(st["iters"][b])
+            Yf, _, stf = s.solve(X, iters=k)
+            assert s.last_kernel == "batched_imma_paired"
+            assert np.array_equal(Yf[b], Y[b], equal_nan=True), (b, k)
+            if conv[b]:
+                assert abs(stf["gap"][b] - st["gap"][b]) <= 2e-2 and abs(stf["kkt"][b] - st["kkt"][b]) <= 1e-3
+        Fd, Fp = s.linear_terms(100)
+    monkeypatch.setenv("PQP_IMMA_PAIRED_TOL", "0")
+    with pqp.Solver(d, prob, **opts) as s:
+        Y1, U1, st1 = s.solve(X, iters=0, primal=True)
+        assert s.last_kernel == "batched_imma"
+    both = conv & (st1["converged"] == 1)
+    assert both.mean() > 0.9
+    assert np.median(np.abs(st["iters"][both].astype(int) - st1["iters"][both].astype(int))) <= 16
+    assert relerr(U[both], U1[both]) <= 1e-3
