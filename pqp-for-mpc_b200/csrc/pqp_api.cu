@@ -471,20 +471,18 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 	if ((rc = dalloc(&h->GQ, (size_t)N * M)) || (rc = dalloc(&h->Q, (size_t)N * h->ldq))) { pqp_destroy(h); return rc; }
 	cudaError_t e = cudaMemsetAsync(h->Q, 0, (size_t)N * h->ldq * sizeof(float), h->stream);
 	/* GQ = Gp*Qp_inv (PQP_CPU.c:492), Qd = GQ*Gp' (PQP_CPU.c:442) */
+	const int tensor_setup = !strict && o.use_tensor_cores && N >= 64 && M >= 32;
+	float *QiT = NULL; /* tcgen05 3xTF32: both operands K-major, so Qp_inv goes in transposed (allocated before the timed span) */
+	if (tensor_setup && (rc = dalloc(&QiT, (size_t)M * M))) { pqp_destroy(h); return rc; }
 	if (e == cudaSuccess) e = cudaEventRecord(h->ev0, h->stream);
 	if (e == cudaSuccess) {
 		if (strict) {
 			e = pqp_launch_matmul_strict(h->GQ, M, h->Gp, M, h->Qp_inv, M, 0, N, M, M, h->stream);
 			if (e == cudaSuccess) e = pqp_launch_matmul_strict(h->Q, h->ldq, h->GQ, M, h->Gp, M, 1, N, M, N, h->stream);
-		} else if (o.use_tensor_cores && N >= 64 && M >= 32) {
-			/* tcgen05 3xTF32: both operands K-major, so Qp_inv goes in transposed */
-			float *QiT = NULL;
-			if ((rc = dalloc(&QiT, (size_t)M * M))) { pqp_destroy(h); return rc; }
+		} else if (tensor_setup) {
 			e = pqp_launch_transpose(QiT, M, h->Qp_inv, M, M, M, h->stream);
 			if (e == cudaSuccess) e = pqp_launch_gemm_umma(h->GQ, M, h->Gp, M, QiT, M, N, M, M, h->stream);
 			if (e == cudaSuccess) e = pqp_launch_gemm_umma(h->Q, h->ldq, h->GQ, M, h->Gp, M, N, M, N, h->stream);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-			cudaFree(QiT);
 			h->launches += 1;
 		} else {
 			e = pqp_launch_matmul_simt(h->GQ, M, h->Gp, M, h->Qp_inv, M, 0, N, M, M, h->stream);
@@ -495,6 +493,7 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 		if (e == cudaSuccess) e = cudaEventSynchronize(h->ev1);
 		if (e == cudaSuccess) e = cudaEventElapsedTime(&h->setup_gemm_ms, h->ev0, h->ev1);
 	}
+	if (QiT) cudaFree(QiT);
 	if (e != cudaSuccess) {
 		snprintf(g_cuda_err, sizeof g_cuda_err, "setup GEMMs -> %s", cudaGetErrorString(e));
 		pqp_destroy(h);
@@ -965,7 +964,7 @@ static int tol_chunked(pqp_handle *h, int B, const float *Y0, float *Y, pqp_stat
 		if (first && fuse_refresh) {
 			h->fp_B = B;
 			if (Md) { /* Md needs the Fp the kernel formed */
-				CK(pqp_launch_md(h->Md, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, h->cur_D, h->cur_Dstride, h->X, B, M,
+				CK(pqp_launch_md(h->Md, h->Tmp, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, h->cur_D, h->cur_Dstride, h->X, B, M,
 						 h->d.nDisH, h->d.nState, h->stream));
 				h->launches++;
 			}
@@ -1030,7 +1029,7 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 		h->fp_B = B;
 		if (want_status) {
 			/* Md needs the Fp the kernel formed: after it.  Jd = 1/2 y'Qd y + Fd'y + Md/2 (computeCost, PQP_CPU.c:648-666) */
-			CK(pqp_launch_md(h->Md, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, h->cur_D, h->cur_Dstride, h->X, B, M,
+			CK(pqp_launch_md(h->Md, h->Tmp, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, h->cur_D, h->cur_Dstride, h->X, B, M,
 					 h->d.nDisH, h->d.nState, h->stream));
 			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, h->Md, h->Kp, h->o.erc, h->o.eac, B, iters + h->iters_base, NULL, h->stream));
 			h->launches += 2;
@@ -1179,7 +1178,7 @@ static int form_linear_terms(pqp_handle *h, const float *X, const float *D, int 
 	}
 	h->fp_B = B;
 	if (want_status) {
-		CK(pqp_launch_md(h->Md, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, Dd, Dstride, h->X, B, M,
+		CK(pqp_launch_md(h->Md, h->Tmp, h->Fp, h->Qp_inv, h->Mp1, h->Mp2, h->Mp3, h->Mp4, h->Mp5, h->Mp6, h->Mp0, Dd, Dstride, h->X, B, M,
 				 nd, nS, h->stream));
 		h->launches++;
 	}

@@ -17,6 +17,8 @@
 #include "pqp_internal.h"
 #include "pqp_umma.cuh"
 
+#include <stdlib.h>
+
 #define GT_M 128
 #define GT_N 128
 #define GT_K 32
@@ -159,6 +161,9 @@ gemm_3xtf32_kernel(float *__restrict__ C, int ldc, const float *__restrict__ A, 
 cudaError_t pqp_launch_gemm_umma(float *C, int ldc, const float *A, int lda, const float *Bt, int ldb, int a, int b, int c,
 				 cudaStream_t s)
 {
+	/* the warp-specialised pipeline (pqp_gemm_umma_ws.cu) for anything but small products; PQP_GEMM_WS=0 keeps this kernel */
+	if (pqp_gemm_umma_ws_wanted(a, b, c) && !(pqp_env("PQP_GEMM_WS") && atoi(pqp_env("PQP_GEMM_WS")) == 0))
+		return pqp_launch_gemm_umma_ws(C, ldc, A, lda, Bt, ldb, a, b, c, s);
 	const size_t smem = sizeof(GemmSmem) + 128;
 	cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;

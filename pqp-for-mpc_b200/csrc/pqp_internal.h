@@ -35,6 +35,9 @@ cudaError_t pqp_launch_matmul_simt(float *C, int ldc, const float *A, int lda, c
 /* tcgen05 3xTF32 GEMM (pqp_gemm_umma.cu): C[a x c] = A[a x b] * Bt[c x b]', both operands K-major */
 cudaError_t pqp_launch_gemm_umma(float *C, int ldc, const float *A, int lda, const float *Bt, int ldb, int a, int b, int c,
 				 cudaStream_t s);
+/* the same product as a warp-specialised pipeline (pqp_gemm_umma_ws.cu): loader/converter warps, one MMA warp, drain warps, 128 x 192 tiles */
+int pqp_gemm_umma_ws_wanted(int a, int b, int c);
+cudaError_t pqp_launch_gemm_umma_ws(float *C, int ldc, const float *A, int lda, const float *Bt, int ldb, int a, int b, int c, cudaStream_t s);
 /* theta_i = max(sum_j max(0,-Q_ij), floor); strict: thread per row, j ascending */
 cudaError_t pqp_launch_theta(float *theta, const float *Q, int ldq, int N, float floor_, int strict, cudaStream_t s);
 /* out[c x r] (ldo) = in[r x c] (ldi) transposed */
@@ -53,7 +56,7 @@ cudaError_t pqp_launch_fd(float *Fd, const float *GQ, const float *Fp, const flo
 cudaError_t pqp_launch_fd_offsets(float *Fd, const float *Kx, const float *X, int nState, const float *Kd, const float *D, int D_stride,
 				  int nd, int B, int N, cudaStream_t s);
 /* Md[b] = Fp' Qp_inv Fp - Mp(x_b) (computeMd PQP_CPU.c:472-479, computeMp :395-428); Mp1==NULL: Mp = Mp0 */
-cudaError_t pqp_launch_md(float *Md, const float *Fp, const float *Qp_inv, const float *Mp1, const float *Mp2,
+cudaError_t pqp_launch_md(float *Md, float *tmp /* [B x M] scratch */, const float *Fp, const float *Qp_inv, const float *Mp1, const float *Mp2,
 			  const float *Mp3, const float *Mp4, const float *Mp5, const float *Mp6, float Mp0,
 			  const float *D, int D_stride, const float *X, int B, int M, int nd, int nState, cudaStream_t s);
 /* U[b] = -(Qp_inv*(Gp'*Y[b] + Fp[b])) (computeUfromY, PQP_CPU.c:352-360); tmp [B x M] scratch */

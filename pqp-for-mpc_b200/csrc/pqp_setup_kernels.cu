@@ -311,21 +311,37 @@ __device__ __forceinline__ float block_sum_256(float v, float *red)
 	return t;
 }
 
+/* t[b][j] = sum_k Fp[b][k] Qp_inv[k][j]: a block takes 32 columns j (lane = column: 128-byte row segments of Qp_inv) of one problem,
+ * its 8 warps take k = w, w+8, ... and are folded through shared memory in warp order (deterministic).  Round 1 walked all M rows
+ * per thread column inside ONE block per problem: M = 2048 meant 16 k dependent loads per thread on a single SM. */
+__global__ void __launch_bounds__(256) md_rowvec_kernel(float *__restrict__ t, const float *__restrict__ Fp, const float *__restrict__ Qp_inv, int M)
+{
+	__shared__ float part[8][33];
+	const int b = blockIdx.y, j = blockIdx.x * 32 + threadIdx.x % 32, w = threadIdx.x / 32;
+	const float *f = Fp + (size_t)b * M;
+	float acc = 0.0f;
+	if (j < M)
+		for (int k = w; k < M; k += 8) acc = fmaf(f[k], Qp_inv[(size_t)k * M + j], acc);
+	part[w][threadIdx.x % 32] = acc;
+	__syncthreads();
+	if (w == 0 && j < M) {
+		float s = part[0][threadIdx.x];
+		for (int u = 1; u < 8; u++) s += part[u][threadIdx.x];
+		t[(size_t)b * M + j] = s;
+	}
+}
+
 __global__ void __launch_bounds__(256)
-md_kernel(float *__restrict__ Md, const float *__restrict__ Fp, const float *__restrict__ Qp_inv,
+md_kernel(float *__restrict__ Md, const float *__restrict__ Fp, const float *__restrict__ t,
 	  const float *__restrict__ Mp1, const float *__restrict__ Mp2, const float *__restrict__ Mp3,
 	  const float *__restrict__ Mp4, const float *__restrict__ Mp5, const float *__restrict__ Mp6, float Mp0,
 	  const float *__restrict__ D, int D_stride, const float *__restrict__ X, int M, int nd, int nState)
 {
 	__shared__ float red[8];
 	const int b = blockIdx.x;
-	const float *f = Fp + (size_t)b * M;
+	const float *f = Fp + (size_t)b * M, *tb = t + (size_t)b * M;
 	float part = 0.0f;
-	for (int j = threadIdx.x; j < M; j += blockDim.x) {
-		float tj = 0.0f;
-		for (int k = 0; k < M; k++) tj = fmaf(f[k], Qp_inv[(size_t)k * M + j], tj);
-		part = fmaf(tj, f[j], part);
-	}
+	for (int j = threadIdx.x; j < M; j += blockDim.x) part = fmaf(tb[j], f[j], part);
 	const float quad = block_sum_256(part, red);
 	float mp = Mp0;
 	if (Mp1) {
@@ -347,11 +363,16 @@ md_kernel(float *__restrict__ Md, const float *__restrict__ Fp, const float *__r
 	if (threadIdx.x == 0) Md[b] = quad - mp;
 }
 
-cudaError_t pqp_launch_md(float *Md, const float *Fp, const float *Qp_inv, const float *Mp1, const float *Mp2,
+/* tmp: [B x M] scratch */
+cudaError_t pqp_launch_md(float *Md, float *tmp, const float *Fp, const float *Qp_inv, const float *Mp1, const float *Mp2,
 			  const float *Mp3, const float *Mp4, const float *Mp5, const float *Mp6, float Mp0, const float *D,
 			  int D_stride, const float *X, int B, int M, int nd, int nState, cudaStream_t s)
 {
-	md_kernel<<<B, 256, 0, s>>>(Md, Fp, Qp_inv, Mp1, Mp2, Mp3, Mp4, Mp5, Mp6, Mp0, D, D_stride, X, M, nd, nState);
+	for (int b0 = 0; b0 < B; b0 += 65535) { /* gridDim.y limit */
+		const int nb = B - b0 < 65535 ? B - b0 : 65535;
+		md_rowvec_kernel<<<dim3((M + 31) / 32, nb), 256, 0, s>>>(tmp + (size_t)b0 * M, Fp + (size_t)b0 * M, Qp_inv, M);
+	}
+	md_kernel<<<B, 256, 0, s>>>(Md, Fp, tmp, Mp1, Mp2, Mp3, Mp4, Mp5, Mp6, Mp0, D, D_stride, X, M, nd, nState);
 	return cudaGetLastError();
 }
 

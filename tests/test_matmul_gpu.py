@@ -25,7 +25,7 @@ def test_strict_engine_is_bit_identical_to_matrixMultiply(pqp, oracle32, a, b, c
             assert np.array_equal(got, want), (tA, tB)
 
 
-@pytest.mark.parametrize("a,b,c", SHAPES + [(1024, 2048, 1024), (8192, 2048, 256)])
+@pytest.mark.parametrize("a,b,c", SHAPES + [(1024, 2048, 1024), (8192, 2048, 256), (257, 65, 193), (1000, 100, 1000), (640, 96, 384)])
 @pytest.mark.parametrize("engine", ["simt", "tensor"])
 def test_fast_engines_fp32_accuracy(pqp, a, b, c, engine):
     rng = np.random.default_rng(a + b + c)
