@@ -190,6 +190,14 @@ __device__ __forceinline__ void tmem_st8_f32(uint32_t taddr, const float *v)
 		     : "memory");
 	asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+/* 32 lanes x 4 columns, no wait (pair with tmem_st_wait) */
+__device__ __forceinline__ void tmem_st4_f32_nowait(uint32_t taddr, const float *v)
+{
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])),
+		     "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+		     : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
