@@ -48,10 +48,13 @@ __device__ __forceinline__ float4 gw_load(const float *__restrict__ G, int ld, i
 {
 	const int r = f / GW_CG, cg = f % GW_CG, gr = row0 + r, gk = k0 + cg * 4;
 	float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef GW_EXP
+	if (GW_EXP & 1) return make_float4(1.f, 2.f, 3.f, 4.f);
+#endif
 	if (gr < nrows) {
 		const float *src = G + (size_t)gr * ld + gk;
 		if (vec && gk + 3 < nk) {
-			v = __ldg(reinterpret_cast<const float4 *>(src));
+			v = __ldcg(reinterpret_cast<const float4 *>(src)); /* L2 only: a 16-deep chunk uses half of each 128-byte line, the tiny L1 left beside 165 KB of shared memory would evict the other half before the next chunk asks for it */
 		} else {
 			if (gk + 0 < nk) v.x = src[0];
 			if (gk + 1 < nk) v.y = src[1];
@@ -63,6 +66,12 @@ __device__ __forceinline__ float4 gw_load(const float *__restrict__ G, int ld, i
 }
 __device__ __forceinline__ void gw_split_store(unsigned char *hi_tile, unsigned char *lo_tile, uint32_t lbo, int f, float4 v)
 {
+#ifdef GW_EXP
+	if (GW_EXP & 2) {
+		if (v.x == 12345.f) *reinterpret_cast<float4 *>(hi_tile) = v;
+		return;
+	}
+#endif
 	const int r = f / GW_CG, cg = f % GW_CG;
 	float4 h, l;
 	umma::tf32_split(v.x, h.x, l.x);
@@ -87,7 +96,17 @@ gemm_3xtf32_ws_kernel(float *__restrict__ C, int ldc, const float *__restrict__ 
 	uint64_t *acc_empty = acc_full + 2;     /* [2] */
 	uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 	const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
-	const int i0 = blockIdx.y * GW_M, j0 = blockIdx.x * GW_N;
+	/* tile order: groups of 8 row blocks, column tiles outermost inside a group -- the ~148 CTAs in flight then share 8 row blocks of A
+	 * and ~18 column tiles of B (30 MB at C3) instead of 4 row blocks and ALL of B (67 MB per wave, re-read from HBM 8x: ncu) */
+	int ti, tj;
+	{
+		const int tx = gridDim.x, ty = gridDim.y, L = blockIdx.y * tx + blockIdx.x;
+		const int grp = L / (8 * tx), within = L - grp * 8 * tx;
+		const int rows = min(8, ty - grp * 8);
+		ti = grp * 8 + within % rows;
+		tj = within / rows;
+	}
+	const int i0 = ti * GW_M, j0 = tj * GW_N;
 	const int nchunks = (b + GW_K - 1) / GW_K;
 	const int nchains = (nchunks + GW_DRAIN - 1) / GW_DRAIN;
 
@@ -168,6 +187,9 @@ gemm_3xtf32_ws_kernel(float *__restrict__ C, int ldc, const float *__restrict__ 
 					const uint32_t oa = (uint32_t)ks * 2u * GW_LBO_A, ob = (uint32_t)ks * 2u * GW_LBO_B;
 					const uint64_t dah = umma::smem_desc(a_hi + oa, GW_LBO_A, GW_SBO), dal = umma::smem_desc(a_lo + oa, GW_LBO_A, GW_SBO);
 					const uint64_t dbh = umma::smem_desc(b_hi + ob, GW_LBO_B, GW_SBO), dbl = umma::smem_desc(b_lo + ob, GW_LBO_B, GW_SBO);
+#ifdef GW_EXP
+					if (GW_EXP & 4) continue;
+#endif
 					umma::mma_tf32(d, dal, dbh, idesc, (!chain_start || ks) ? 1u : 0u); /* small terms first */
 					umma::mma_tf32(d, dah, dbl, idesc, 1u);
 					umma::mma_tf32(d, dah, dbh, idesc, 1u);
@@ -202,10 +224,16 @@ gemm_3xtf32_ws_kernel(float *__restrict__ C, int ldc, const float *__restrict__ 
 		}
 		const int gi = i0 + 32 * q + lane;
 		if (gi < a) {
+			/* streaming stores: C (268 MB at C3) must not push the operands out of L2; 16 bytes per store where the row allows it */
 			float *dst = C + (size_t)gi * ldc + j0 + cb * 64;
+			if ((ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && j0 + cb * 64 + 64 <= c) {
 #pragma unroll
-			for (int e = 0; e < 64; e++)
-				if (j0 + cb * 64 + e < c) dst[e] = acc[e];
+				for (int e = 0; e < 64; e += 4) __stcs(reinterpret_cast<float4 *>(dst + e), make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]));
+			} else {
+#pragma unroll
+				for (int e = 0; e < 64; e++)
+					if (j0 + cb * 64 + e < c) __stcs(dst + e, acc[e]);
+			}
 		}
 	}
 	umma::tc_fence_before();

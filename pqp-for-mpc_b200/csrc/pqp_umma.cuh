@@ -121,14 +121,16 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar)
 /* ---- 3xTF32 split ------------------------------------------------------------------------------------ */
 /*
  * x = hi + lo + O(2^-24 |x|), both exactly representable in tf32 (10 explicit mantissa bits), so the
- * tensor core's truncation of the low 13 bits is a no-op.  hi is x rounded to nearest; lo is the exact
+ * tensor core's truncation of the low 13 bits is a no-op.  hi is x rounded to nearest (cvt.rna.tf32.f32); lo is the exact
  * remainder rounded to nearest.  a*b ~= hi_a*hi_b + hi_a*lo_b + lo_a*hi_b  (error <= ~2^-22 |ab|).
  */
 __device__ __forceinline__ float tf32_rn(float x)
 {
-	uint32_t u = __float_as_uint(x);
-	u += 0x00000FFFu + ((u >> 13) & 1u); /* round to nearest even at bit 13 */
-	return __uint_as_float(u & 0xFFFFE000u);
+	/* one instruction (round to nearest, ties away from zero; low 13 bits zero) instead of four integer operations: the setup GEMM's
+	 * converter warps were the bound of that kernel (round 2) */
+	uint32_t u;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+	return __uint_as_float(u);
 }
 __device__ __forceinline__ void tf32_split(float x, float &hi, float &lo)
 {
