@@ -408,11 +408,19 @@ def single_leg(ctx, wname, *, sampler, cpu, parity, setup):
         tp = tensor_peaks()
         flop = 2.0 * N * M * M + 2.0 * N * N * M
         g_ms = s.setup_gemm_ms
-        block["setup"] = {"what": "convertToDual's GEMMs on the device: GQ = Gp*Qp_inv, Qd = GQ*Gp' (PQP_CPU.c:492, :442), tcgen05 3xTF32",
-                          "ms": g_ms, "flop": flop, "tflops_fp32_equivalent": flop / (g_ms * 1e-3) / 1e12,
-                          "roofline": {"bound": "tensor", "achieved": 3.0 * flop / (g_ms * 1e-3) / 1e12, "peak": tp["tf32"], "unit": "TFLOP/s",
-                                       "frac": 3.0 * flop / (g_ms * 1e-3) / 1e12 / tp["tf32"], "peak_source": tp["source"],
-                                       "note": "achieved counts the three tf32 products (hi*hi, hi*lo, lo*hi) per fp32 product"}}
+        # a symmetric Qp_inv: only the 128 x 192 tiles that touch the upper triangle of Qd are multiplied (and mirrored)
+        mirrored = s.setup_mirrored
+        tiles_all = -(-N // 128) * -(-N // 192)
+        tiles = sum(1 for ti in range(-(-N // 128)) for tj in range(-(-N // 192)) if 192 * tj + 191 >= 128 * ti) if mirrored else tiles_all
+        done = 2.0 * N * M * M + 2.0 * N * N * M * tiles / tiles_all
+        block["setup"] = {"what": "convertToDual's GEMMs on the device: GQ = Gp*Qp_inv, Qd = GQ*Gp' (PQP_CPU.c:492, :442), tcgen05 3xTF32"
+                                  + ("; Qp_inv is symmetric, so Qd is built from the tiles of its upper triangle and mirrored" if mirrored else ""),
+                          "ms": g_ms, "flop": flop, "tflops_fp32_equivalent": flop / (g_ms * 1e-3) / 1e12, "mirrored": bool(mirrored),
+                          "tiles_multiplied": tiles, "tiles_of_the_full_product": tiles_all,
+                          "roofline": {"bound": "tensor", "achieved": 3.0 * done / (g_ms * 1e-3) / 1e12, "peak": tp["tf32"], "unit": "TFLOP/s",
+                                       "frac": 3.0 * done / (g_ms * 1e-3) / 1e12 / tp["tf32"], "peak_source": tp["source"],
+                                       "note": "achieved counts the three tf32 products (hi*hi, hi*lo, lo*hi) per fp32 product of the tiles "
+                                               "that were multiplied; tflops_fp32_equivalent counts the whole product"}}
     if ctx.rank == 0 and (cpu or parity):
         engine, kind = cpu_engine()
         Qd_host, _, _ = s.dual(want_gq=False)

@@ -291,6 +291,10 @@ float pqp_last_solve_ms(pqp_handle *h);
 /* device time, in ms, of the two GEMMs of convertToDual (GQ = Gp*Qp_inv, Qd = GQ*Gp'; PQP_CPU.c:492, :442) inside pqp_setup
  * (2*N*M*M + 2*N*N*M flop); 0 for a handle built by pqp_setup_dual */
 float pqp_setup_gemm_ms(pqp_handle *h);
+/* 1 when pqp_setup built Qd from the tiles of its upper triangle (Qp_inv symmetric element for element, FAST order, tensor-core
+ * setup, exploit_symmetry): every element above the diagonal is one sum stored twice; the multiplied share of the N x N product
+ * is the tiles of 128 x 192 that touch the upper triangle.  0 otherwise. */
+int pqp_setup_mirrored(pqp_handle *h);
 /* how many of this library's kernels the handle has launched so far */
 long long pqp_launch_count(pqp_handle *h);
 /* name of the iteration kernel the last solve used ("gemv_tma_stream", "gemv_strict", "batched_imma", "batched_simt", ...) */

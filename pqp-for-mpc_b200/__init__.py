@@ -70,7 +70,7 @@ ABI_SYMBOLS = (
     "pqp_setup", "pqp_setup_dual", "pqp_destroy", "pqp_solve_batch", "pqp_solve_dual", "pqp_recover_primal",
     "pqp_solve_batch_primal", "pqp_get_dual", "pqp_get_linear_terms", "pqp_get_stream", "pqp_last_solve_ms",
     "pqp_launch_count", "pqp_last_kernel", "pqp_device_qd", "pqp_matmul", "pqp_shift_duals", "pqp_output_offsets", "pqp_update_y2",
-    "pqp_solve_dual_full", "pqp_set_constraint_bounds", "pqp_compute_fp", "pqp_compute_cost", "pqp_compute_md", "pqp_compute_u_from_y", "pqp_setup_gemm_ms",
+    "pqp_solve_dual_full", "pqp_set_constraint_bounds", "pqp_compute_fp", "pqp_compute_cost", "pqp_compute_md", "pqp_compute_u_from_y", "pqp_setup_gemm_ms", "pqp_setup_mirrored",
 )
 MM_STRICT, MM_SIMT, MM_TENSOR = 0, 1, 2
 
@@ -113,6 +113,8 @@ def lib() -> C.CDLL:
         L.pqp_last_solve_ms.argtypes = [C.c_void_p]
         L.pqp_setup_gemm_ms.restype = C.c_float
         L.pqp_setup_gemm_ms.argtypes = [C.c_void_p]
+        L.pqp_setup_mirrored.restype = C.c_int
+        L.pqp_setup_mirrored.argtypes = [C.c_void_p]
         L.pqp_launch_count.restype = C.c_longlong
         L.pqp_launch_count.argtypes = [C.c_void_p]
         L.pqp_device_qd.restype = C.c_void_p
@@ -398,6 +400,11 @@ class Solver:
     @property
     def setup_gemm_ms(self) -> float:
         return float(lib().pqp_setup_gemm_ms(self._h))
+
+    @property
+    def setup_mirrored(self) -> bool:
+        """Qd was built from the tiles of its upper triangle (symmetric Qp_inv) and mirrored."""
+        return bool(lib().pqp_setup_mirrored(self._h))
 
     @property
     def launch_count(self) -> int:

@@ -104,6 +104,7 @@ struct pqp_handle {
 	long long launches;
 	const char *last_kernel;
 	pqp_env_snapshot env; /* PQP_* knobs as they were when the handle was created */
+	int qd_mirrored;       /* pqp_setup built Qd from the tiles of its upper triangle (symmetric Qp_inv): both copies of a pair are one sum */
 	float setup_gemm_ms;   /* device time of the two dual-construction GEMMs (GQ, Qd) in pqp_setup */
 	size_t l2_limit_saved; /* cudaLimitPersistingL2CacheSize before this handle changed it */
 	int l2_limit_changed;
@@ -474,6 +475,13 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 	const int tensor_setup = !strict && o.use_tensor_cores && N >= 64 && M >= 32;
 	float *QiT = NULL; /* tcgen05 3xTF32: both operands K-major, so Qp_inv goes in transposed (allocated before the timed span) */
 	if (tensor_setup && (rc = dalloc(&QiT, (size_t)M * M))) { pqp_destroy(h); return rc; }
+	/* Qd = Gp Qp_inv Gp' is symmetric in exact arithmetic whenever Qp_inv is: then only the tiles of the upper triangle are multiplied
+	 * and every element above the diagonal is stored twice (pqp_gemm_umma_ws.cu) -- half the tensor work, and a Qd that is symmetric
+	 * bit for bit.  Whether Qp_inv is symmetric is counted on the device and read by the GEMM there: no host round trip. */
+	const char *esym = pqp_env("PQP_GEMM_SYM");
+	const int sym_build = tensor_setup && o.exploit_symmetry && pqp_gemm_umma_ws_wanted(N, M, N) && !(esym && atoi(esym) == 0);
+	unsigned *qsym_bad = NULL, qsym_bad_host = 1;
+	if (sym_build && (rc = dalloc(&qsym_bad, 1))) { cudaFree(QiT); pqp_destroy(h); return rc; }
 	if (e == cudaSuccess) e = cudaEventRecord(h->ev0, h->stream);
 	if (e == cudaSuccess) {
 		if (strict) {
@@ -482,7 +490,14 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 		} else if (tensor_setup) {
 			e = pqp_launch_transpose(QiT, M, h->Qp_inv, M, M, M, h->stream);
 			if (e == cudaSuccess) e = pqp_launch_gemm_umma(h->GQ, M, h->Gp, M, QiT, M, N, M, M, h->stream);
-			if (e == cudaSuccess) e = pqp_launch_gemm_umma(h->Q, h->ldq, h->GQ, M, h->Gp, M, N, M, N, h->stream);
+			if (sym_build) {
+				if (e == cudaSuccess) e = pqp_launch_sym_check(h->Qp_inv, M, M, qsym_bad, h->stream);
+				if (e == cudaSuccess) e = pqp_launch_gemm_umma_ws(h->Q, h->ldq, h->GQ, M, h->Gp, M, N, M, N, qsym_bad, h->stream);
+				if (e == cudaSuccess) e = cudaMemcpyAsync(&qsym_bad_host, qsym_bad, sizeof qsym_bad_host, cudaMemcpyDeviceToHost, h->stream);
+				h->launches += 1;
+			} else if (e == cudaSuccess) {
+				e = pqp_launch_gemm_umma(h->Q, h->ldq, h->GQ, M, h->Gp, M, N, M, N, h->stream);
+			}
 			h->launches += 1;
 		} else {
 			e = pqp_launch_matmul_simt(h->GQ, M, h->Gp, M, h->Qp_inv, M, 0, N, M, M, h->stream);
@@ -493,14 +508,16 @@ int pqp_setup(pqp_handle **out, const pqp_dims *dims, const pqp_host_problem *p,
 		if (e == cudaSuccess) e = cudaEventSynchronize(h->ev1);
 		if (e == cudaSuccess) e = cudaEventElapsedTime(&h->setup_gemm_ms, h->ev0, h->ev1);
 	}
+	if (qsym_bad) cudaFree(qsym_bad);
+	h->qd_mirrored = sym_build && e == cudaSuccess && qsym_bad_host == 0;
 	if (QiT) cudaFree(QiT);
 	if (e != cudaSuccess) {
 		snprintf(g_cuda_err, sizeof g_cuda_err, "setup GEMMs -> %s", cudaGetErrorString(e));
 		pqp_destroy(h);
 		return PQP_ERR_CUDA;
 	}
-	if (!strict && o.exploit_symmetry) {
-		/* Gp Qp_inv Gp' is symmetric in exact arithmetic; its two fp32 copies of an element are different sums.  One value per
+	if (!strict && o.exploit_symmetry && !h->qd_mirrored) {
+		/* (a Qd built from its upper triangle is symmetric already.)  Gp Qp_inv Gp' is symmetric in exact arithmetic; its two fp32 copies of an element are different sums.  One value per
 		 * pair (their mean) when all pairs agree to rounding: then every loop sees a symmetric Qd and the single-problem loop can
 		 * run from the upper triangle.  A Qd whose copies differ by more than rounding (an unsymmetric Qp_inv) is left as computed. */
 		unsigned *bad_dev = NULL, bad = 0;
@@ -1532,6 +1549,7 @@ float pqp_last_solve_ms(pqp_handle *h)
 }
 
 float pqp_setup_gemm_ms(pqp_handle *h) { return h ? h->setup_gemm_ms : -1.0f; }
+int pqp_setup_mirrored(pqp_handle *h) { return h ? h->qd_mirrored : 0; }
 long long pqp_launch_count(pqp_handle *h) { return h ? h->launches : 0; }
 const char *pqp_last_kernel(pqp_handle *h) { return h ? h->last_kernel : "none"; }
 const float *pqp_device_qd(pqp_handle *h, int *ld)

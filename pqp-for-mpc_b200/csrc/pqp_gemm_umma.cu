@@ -162,8 +162,7 @@ cudaError_t pqp_launch_gemm_umma(float *C, int ldc, const float *A, int lda, con
 				 cudaStream_t s)
 {
 	/* the warp-specialised pipeline (pqp_gemm_umma_ws.cu) for anything but small products; PQP_GEMM_WS=0 keeps this kernel */
-	if (pqp_gemm_umma_ws_wanted(a, b, c) && !(pqp_env("PQP_GEMM_WS") && atoi(pqp_env("PQP_GEMM_WS")) == 0))
-		return pqp_launch_gemm_umma_ws(C, ldc, A, lda, Bt, ldb, a, b, c, s);
+	if (pqp_gemm_umma_ws_wanted(a, b, c)) return pqp_launch_gemm_umma_ws(C, ldc, A, lda, Bt, ldb, a, b, c, NULL, s);
 	const size_t smem = sizeof(GemmSmem) + 128;
 	cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;

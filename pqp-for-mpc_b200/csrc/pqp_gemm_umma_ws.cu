@@ -18,6 +18,8 @@
  * accumulator registers per thread.  Roofline: tensor (tf32): 3 MMA flop per algorithmic flop.
  */
 #include "pqp_internal.h"
+
+#include <stdlib.h>
 #include "pqp_umma.cuh"
 
 #define GW_M 128
@@ -48,9 +50,6 @@ __device__ __forceinline__ float4 gw_load(const float *__restrict__ G, int ld, i
 {
 	const int r = f / GW_CG, cg = f % GW_CG, gr = row0 + r, gk = k0 + cg * 4;
 	float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#ifdef GW_EXP
-	if (GW_EXP & 1) return make_float4(1.f, 2.f, 3.f, 4.f);
-#endif
 	if (gr < nrows) {
 		const float *src = G + (size_t)gr * ld + gk;
 		if (vec && gk + 3 < nk) {
@@ -66,12 +65,6 @@ __device__ __forceinline__ float4 gw_load(const float *__restrict__ G, int ld, i
 }
 __device__ __forceinline__ void gw_split_store(unsigned char *hi_tile, unsigned char *lo_tile, uint32_t lbo, int f, float4 v)
 {
-#ifdef GW_EXP
-	if (GW_EXP & 2) {
-		if (v.x == 12345.f) *reinterpret_cast<float4 *>(hi_tile) = v;
-		return;
-	}
-#endif
 	const int r = f / GW_CG, cg = f % GW_CG;
 	float4 h, l;
 	umma::tf32_split(v.x, h.x, l.x);
@@ -84,9 +77,10 @@ __device__ __forceinline__ void gw_split_store(unsigned char *hi_tile, unsigned 
 }
 } /* namespace */
 
+/* (registers are handed out per 4 warps: the 21 warps count as 24, so 80 registers per thread is the most a launch accepts) */
 __global__ void __launch_bounds__(GW_THREADS, 1)
 gemm_3xtf32_ws_kernel(float *__restrict__ C, int ldc, const float *__restrict__ A, int lda, const float *__restrict__ Bt, int ldb, int a, int b,
-		      int c)
+		      int c, const unsigned *__restrict__ sym_bad)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	unsigned char *ring = smem_raw; /* [stage][A_hi | A_lo | B_hi | B_lo] */
@@ -107,6 +101,11 @@ gemm_3xtf32_ws_kernel(float *__restrict__ C, int ldc, const float *__restrict__ 
 		tj = within / rows;
 	}
 	const int i0 = ti * GW_M, j0 = tj * GW_N;
+	/* symmetric product (C = X S X' with S symmetric: Qd = Gp Qp_inv Gp'): only the tiles that touch the upper triangle are multiplied;
+	 * their elements above the diagonal are stored twice, as C_ij and as C_ji.  *sym_bad is the device-side count of unequal pairs
+	 * of S (pqp_launch_sym_check), so the decision needs no host round trip. */
+	const bool sym = sym_bad != nullptr && a == c && __ldg(sym_bad) == 0u;
+	if (sym && j0 + GW_N - 1 < i0) return; /* whole tile below the diagonal: its mirror image writes it */
 	const int nchunks = (b + GW_K - 1) / GW_K;
 	const int nchains = (nchunks + GW_DRAIN - 1) / GW_DRAIN;
 
@@ -187,9 +186,6 @@ gemm_3xtf32_ws_kernel(float *__restrict__ C, int ldc, const float *__restrict__ 
 					const uint32_t oa = (uint32_t)ks * 2u * GW_LBO_A, ob = (uint32_t)ks * 2u * GW_LBO_B;
 					const uint64_t dah = umma::smem_desc(a_hi + oa, GW_LBO_A, GW_SBO), dal = umma::smem_desc(a_lo + oa, GW_LBO_A, GW_SBO);
 					const uint64_t dbh = umma::smem_desc(b_hi + ob, GW_LBO_B, GW_SBO), dbl = umma::smem_desc(b_lo + ob, GW_LBO_B, GW_SBO);
-#ifdef GW_EXP
-					if (GW_EXP & 4) continue;
-#endif
 					umma::mma_tf32(d, dal, dbh, idesc, (!chain_start || ks) ? 1u : 0u); /* small terms first */
 					umma::mma_tf32(d, dah, dbl, idesc, 1u);
 					umma::mma_tf32(d, dah, dbh, idesc, 1u);
@@ -223,17 +219,25 @@ gemm_3xtf32_ws_kernel(float *__restrict__ C, int ldc, const float *__restrict__ 
 			if (lane == 0) umma::mbar_arrive(&acc_empty[buf]);
 		}
 		const int gi = i0 + 32 * q + lane;
+		const int jb = j0 + cb * 64;
 		if (gi < a) {
 			/* streaming stores: C (268 MB at C3) must not push the operands out of L2; 16 bytes per store where the row allows it */
-			float *dst = C + (size_t)gi * ldc + j0 + cb * 64;
-			if ((ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && j0 + cb * 64 + 64 <= c) {
+			float *dst = C + (size_t)gi * ldc + jb;
+			const bool whole = !sym || jb >= i0 + GW_M; /* no element of this block lies below the diagonal */
+			if (whole && (ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0) && jb + 64 <= c) {
 #pragma unroll
 				for (int e = 0; e < 64; e += 4) __stcs(reinterpret_cast<float4 *>(dst + e), make_float4(acc[e], acc[e + 1], acc[e + 2], acc[e + 3]));
 			} else {
 #pragma unroll
 				for (int e = 0; e < 64; e++)
-					if (j0 + cb * 64 + e < c) __stcs(dst + e, acc[e]);
+					if (jb + e < c && (whole || jb + e >= gi)) __stcs(dst + e, acc[e]);
 			}
+		}
+		if (sym) {
+			/* the mirror image: lane = row of the tile, so C_ji of one column j is 32 consecutive floats over the warp */
+#pragma unroll
+			for (int e = 0; e < 64; e++)
+				if (gi < a && jb + e < c && jb + e > gi) __stcs(C + (size_t)(jb + e) * ldc + gi, acc[e]);
 		}
 	}
 	umma::tc_fence_before();
@@ -242,14 +246,19 @@ gemm_3xtf32_ws_kernel(float *__restrict__ C, int ldc, const float *__restrict__ 
 }
 
 /* worth it from a few tiles per SM on; small products stay on the simpler kernel */
-int pqp_gemm_umma_ws_wanted(int a, int b, int c) { return a >= 256 && c >= 192 && b >= 64; }
+int pqp_gemm_umma_ws_wanted(int a, int b, int c)
+{
+	const char *e = pqp_env("PQP_GEMM_WS"); /* PQP_GEMM_WS=0 keeps round 1's kernel */
+	return a >= 256 && c >= 192 && b >= 64 && !(e && atoi(e) == 0);
+}
 
-cudaError_t pqp_launch_gemm_umma_ws(float *C, int ldc, const float *A, int lda, const float *Bt, int ldb, int a, int b, int c, cudaStream_t s)
+cudaError_t pqp_launch_gemm_umma_ws(float *C, int ldc, const float *A, int lda, const float *Bt, int ldb, int a, int b, int c,
+				    const unsigned *sym_bad, cudaStream_t s)
 {
 	const size_t smem = (size_t)GW_STAGES * GW_STAGE + 128;
 	cudaError_t e = cudaFuncSetAttribute(gemm_3xtf32_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return e;
 	dim3 grid((c + GW_N - 1) / GW_N, (a + GW_M - 1) / GW_M);
-	gemm_3xtf32_ws_kernel<<<grid, GW_THREADS, smem, s>>>(C, ldc, A, lda, Bt, ldb, a, b, c);
+	gemm_3xtf32_ws_kernel<<<grid, GW_THREADS, smem, s>>>(C, ldc, A, lda, Bt, ldb, a, b, c, sym_bad);
 	return cudaGetLastError();
 }

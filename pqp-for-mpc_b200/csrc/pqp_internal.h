@@ -37,7 +37,10 @@ cudaError_t pqp_launch_gemm_umma(float *C, int ldc, const float *A, int lda, con
 				 cudaStream_t s);
 /* the same product as a warp-specialised pipeline (pqp_gemm_umma_ws.cu): loader/converter warps, one MMA warp, drain warps, 128 x 192 tiles */
 int pqp_gemm_umma_ws_wanted(int a, int b, int c);
-cudaError_t pqp_launch_gemm_umma_ws(float *C, int ldc, const float *A, int lda, const float *Bt, int ldb, int a, int b, int c, cudaStream_t s);
+/* sym_bad != NULL and a == c: the product is symmetric in exact arithmetic provided *sym_bad (device memory: the count of unequal pairs
+ * of the inner symmetric factor, pqp_launch_sym_check) is zero; then only the upper-triangle tiles are multiplied and mirrored */
+cudaError_t pqp_launch_gemm_umma_ws(float *C, int ldc, const float *A, int lda, const float *Bt, int ldb, int a, int b, int c,
+				    const unsigned *sym_bad, cudaStream_t s);
 /* theta_i = max(sum_j max(0,-Q_ij), floor); strict: thread per row, j ascending */
 cudaError_t pqp_launch_theta(float *theta, const float *Q, int ldq, int N, float floor_, int strict, cudaStream_t s);
 /* out[c x r] (ldo) = in[r x c] (ldi) transposed */

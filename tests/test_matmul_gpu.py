@@ -63,3 +63,34 @@ def test_setup_uses_tensor_cores_and_matches_oracle_dual(pqp, gold_random):
         Qd0, th0, GQ0 = s.dual()
     assert relerr(Qd, g[f"{t}_Qd"]) <= 2e-6 and relerr(Qd0, g[f"{t}_Qd"]) <= 2e-6
     assert relerr(th, g[f"{t}_theta"]) <= 2e-6
+
+
+@pytest.mark.parametrize("N,M", [(640, 96), (1000, 130), (2048, 256)])
+def test_setup_builds_a_symmetric_dual_from_its_upper_triangle(pqp, N, M):
+    """Qd = Gp Qp_inv Gp' (PQP_CPU.c:492, :442) with a symmetric, dense Qp_inv: pqp_setup multiplies only the tiles of the upper
+    triangle and stores every element above the diagonal twice.  The upper triangle must equal the full product's bit for bit, the
+    lower must be its mirror image, and the whole must be the float64 product to fp32 accuracy.  An unsymmetric Qp_inv (not a QP,
+    but the reference would multiply it) takes the full product."""
+    rng = np.random.default_rng(N + M)
+    R = rng.standard_normal((M, M))
+    Qs = (R @ R.T / M + np.eye(M)).astype(np.float32)
+    Qs = ((Qs + Qs.T) * np.float32(0.5)).astype(np.float32)
+    assert np.array_equal(Qs, Qs.T)
+    Gp = rng.standard_normal((N, M)).astype(np.float32)
+    prob = dict(Qp_inv=Qs, Gp=Gp, Kp=np.ones(N, np.float32), Fp=rng.standard_normal(M).astype(np.float32), Mp0=0.0)
+    with pqp.Solver(pqp.dims_plain(M, N), prob) as s:
+        Qd, _, _ = s.dual()
+    with pqp.Solver(pqp.dims_plain(M, N), prob, exploit_symmetry=0) as s:
+        Qfull, _, _ = s.dual()
+    assert np.array_equal(Qd, Qd.T)
+    iu = np.triu_indices(N)
+    assert np.array_equal(Qd[iu], Qfull[iu])
+    want = Gp.astype(np.float64) @ Qs.astype(np.float64) @ Gp.astype(np.float64).T
+    assert relerr(Qd, want) <= 4e-6
+    Qu = Qs.copy()
+    Qu[0, 1] += np.float32(0.25)
+    prob_u = dict(prob, Qp_inv=Qu)
+    with pqp.Solver(pqp.dims_plain(M, N), prob_u) as s:
+        Qd_u, _, _ = s.dual()
+    want_u = Gp.astype(np.float64) @ Qu.astype(np.float64) @ Gp.astype(np.float64).T
+    assert relerr(Qd_u, want_u) <= 4e-6 and not np.array_equal(Qd_u, Qd_u.T)
