@@ -85,6 +85,8 @@ struct pqp_handle {
 	float *tol_ws;      /* run-to-tolerance on the paired kernel: evaluation partials | resume maxima [cap] | kept duals [cap x N] */
 	unsigned *tol_flags; /* frozen [cap] | newly [cap] | remaining [1] */
 	int tol_cap;
+	unsigned *tol_rem_host; /* [2] pinned: "problems still running" after chunk k lands in slot k & 1 */
+	cudaEvent_t tol_ev[2];  /* recorded behind that copy */
 	float *acc_ws;      /* [3][cap][N] scratch of the acceleration step (opts.accelerate), allocated on first use */
 	int acc_cap;
 	int iters_base;     /* updates applied by earlier chunks of the solve in progress (reported in pqp_status.iters) */
@@ -596,6 +598,11 @@ void pqp_destroy(pqp_handle *h)
 			 h->sym.units, h->sym.cta_u0, h->sym.cta_j0, h->sym.strip_c0, h->sym.strip_c1, h->sym.rowpart, h->sym.colpart };
 	for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++)
 		if (ptrs[i]) cudaFree(ptrs[i]);
+	if (h->tol_rem_host) {
+		cudaFreeHost(h->tol_rem_host);
+		cudaEventDestroy(h->tol_ev[0]);
+		cudaEventDestroy(h->tol_ev[1]);
+	}
 	if (h->ev0) cudaEventDestroy(h->ev0);
 	if (h->ev1) cudaEventDestroy(h->ev1);
 	if (h->stream) cudaStreamDestroy(h->stream);
@@ -952,12 +959,21 @@ static int tol_chunked(pqp_handle *h, int B, const float *Y0, float *Y, pqp_stat
 			return rc;
 		h->tol_cap = h->cap;
 	}
+	if (!h->tol_rem_host) {
+		CK(cudaMallocHost((void **)&h->tol_rem_host, 2 * sizeof(unsigned)));
+		CK(cudaEventCreateWithFlags(&h->tol_ev[0], cudaEventDisableTiming));
+		CK(cudaEventCreateWithFlags(&h->tol_ev[1], cudaEventDisableTiming));
+	}
 	float *part = h->tol_ws, *mres = part + pqp_paired_eval_part_floats(h->cap), *Yres = mres + h->cap;
 	unsigned *frozen = h->tol_flags, *newly = frozen + h->cap, *remaining = newly + h->cap;
 	CK(cudaMemsetAsync(frozen, 0, (size_t)B * sizeof(unsigned), h->stream));
 	if (Y0) CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
 	const int every = h->o.check_every > 0 ? h->o.check_every : 1, cap_it = h->o.max_iters > 0 ? h->o.max_iters : 1;
-	int count = 0, first = 1;
+	/* Chunk k+1 is queued BEFORE the count of chunk k is read: the device runs chunk after chunk without waiting for the host, and the
+	 * host learns one chunk late that everybody had passed.  The chunk too many is harmless -- a problem that has passed is frozen: its
+	 * kept duals and status are never touched again -- and costs check_every updates once per solve instead of a stream round trip
+	 * per chunk. */
+	int count = 0, first = 1, k = 0;
 	CK(cudaEventRecord(h->ev0, h->stream));
 	for (;;) {
 		const int n = cap_it - count < every ? cap_it - count : every;
@@ -988,11 +1004,15 @@ static int tol_chunked(pqp_handle *h, int B, const float *Y0, float *Y, pqp_stat
 		}
 		CK(pqp_launch_paired_tol_decide(part, Md, h->st, frozen, newly, remaining, Yres, h->Y, B, N, count, cap_it, h->o.eaj, h->o.erj, h->stream));
 		h->launches += 2;
-		unsigned rem = 0;
-		CK(cudaMemcpyAsync(&rem, remaining, sizeof rem, cudaMemcpyDeviceToHost, h->stream));
-		CK(cudaStreamSynchronize(h->stream));
+		CK(cudaMemcpyAsync(&h->tol_rem_host[k & 1], remaining, sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+		CK(cudaEventRecord(h->tol_ev[k & 1], h->stream));
 		first = 0;
-		if (rem == 0) break;
+		if (k > 0) {
+			CK(cudaEventSynchronize(h->tol_ev[(k - 1) & 1]));
+			if (h->tol_rem_host[(k - 1) & 1] == 0) break; /* everybody had passed a chunk ago */
+		}
+		if (count >= cap_it) break; /* the cap: the decide kernel has frozen whoever was left */
+		k++;
 	}
 	CK(cudaEventRecord(h->ev1, h->stream));
 	h->ev_valid = 1;
