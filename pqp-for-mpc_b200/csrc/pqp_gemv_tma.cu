@@ -49,21 +49,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-/* bounded (seconds): a protocol bug traps instead of hanging the device; the counter only exists on the failing path */
+/* bounded (10 s of %globaltimer): a protocol bug traps instead of hanging the device; the timer is only read on the failing path */
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	asm volatile(
 		"{\n\t"
 		".reg .pred p;\n\t"
-		".reg .u32 n;\n\t"
+		".reg .u64 t0, t1;\n\t"
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
 		"@p bra WAIT_DONE;\n\t"
-		"mov.u32 n, 0;\n\t"
+		"mov.u64 t0, %%globaltimer;\n\t"
 		"WAIT_LOOP:\n\t"
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
 		"@p bra WAIT_DONE;\n\t"
-		"add.u32 n, n, 1;\n\t"
-		"setp.lt.u32 p, n, 0x4000000;\n\t"
+		"mov.u64 t1, %%globaltimer;\n\t"
+		"sub.u64 t1, t1, t0;\n\t"
+		"setp.lt.u64 p, t1, 10000000000;\n\t"
 		"@p bra WAIT_LOOP;\n\t"
 		"trap;\n\t"
 		"WAIT_DONE:\n\t"

@@ -258,15 +258,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity
 	asm volatile(
 		"{\n\t"
 		".reg .pred p;\n\t"
-		".reg .u32 n;\n\t"
+		".reg .u64 t0, t1;\n\t"
 		"mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
 		"@p bra PAIR_DONE;\n\t"
-		"mov.u32 n, 0;\n\t"
+		"mov.u64 t0, %%globaltimer;\n\t"
 		"PAIR_WAIT:\n\t"
 		"mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
 		"@p bra PAIR_DONE;\n\t"
-		"add.u32 n, n, 1;\n\t"
-		"setp.lt.u32 p, n, " PQP_MBAR_SPIN_LIMIT ";\n\t"
+		"mov.u64 t1, %%globaltimer;\n\t"
+		"sub.u64 t1, t1, t0;\n\t"
+		"setp.lt.u64 p, t1, 10000000000;\n\t"
 		"@p bra PAIR_WAIT;\n\t"
 		"trap;\n\t" /* bounded like umma::mbar_wait */
 		"PAIR_DONE:\n\t"

@@ -33,24 +33,23 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
-/* Bounded: a wait that fails PQP_MBAR_SPIN_LIMIT times in a row (seconds; every legitimate wait in these kernels is microseconds)
- * traps -- a protocol bug then surfaces as a CUDA error from the call instead of a hung device.  The counter only exists on the
- * failing path. */
-#define PQP_MBAR_SPIN_LIMIT "0x4000000"
+/* Bounded: a wait that has failed for 10 s of %globaltimer (every legitimate wait in these kernels is microseconds) traps -- a
+ * protocol bug then surfaces as a CUDA error from the call instead of a hung device.  The timer is only read on the failing path. */
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
 	asm volatile(
 		"{\n\t"
 		".reg .pred p;\n\t"
-		".reg .u32 n;\n\t"
+		".reg .u64 t0, t1;\n\t"
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
 		"@p bra UMMA_DONE;\n\t"
-		"mov.u32 n, 0;\n\t"
+		"mov.u64 t0, %%globaltimer;\n\t"
 		"UMMA_WAIT:\n\t"
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
 		"@p bra UMMA_DONE;\n\t"
-		"add.u32 n, n, 1;\n\t"
-		"setp.lt.u32 p, n, " PQP_MBAR_SPIN_LIMIT ";\n\t"
+		"mov.u64 t1, %%globaltimer;\n\t"
+		"sub.u64 t1, t1, t0;\n\t"
+		"setp.lt.u64 p, t1, 10000000000;\n\t"
 		"@p bra UMMA_WAIT;\n\t"
 		"trap;\n\t"
 		"UMMA_DONE:\n\t"
