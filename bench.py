@@ -12,6 +12,8 @@ Default (--workload all): the line every N of the driver's 1/2/4/8-GPU sweep sha
              stated on.  A single problem does not shard ("replicas only"): every rank solves its own replica.
   "batched_c4"  BASELINE config 4: 4096 states per GPU (weak scaling), the launch the committed ncu capture is of.
   "onchip"   BASELINE config 2: N = 1024, M = 512, seed 12345 (Q lives on chip; exchange-latency bound).
+  "one_mpc_sized_problem"  ONE problem of config 4's size (N = 480, M = 120: what a single controller solves per period) on the
+             one-cluster kernel (16 SMs, y exchanged through distributed shared memory): latency only.
   "setup"    the x-independent dual construction (convertToDual's two GEMMs on tcgen05 3xTF32) of the "single" instance.
 --workload c1|c2|c3|c4|c5 makes that config the top level (ncu captures, sweeps); c1 = the shipped example, 312 updates.
 
@@ -52,6 +54,8 @@ WORKLOADS = {
     "c2": dict(kind="single", N=1024, M=512, seed=12345),
     "c3": dict(kind="single", N=8192, M=2048, seed=12346),
     "c4": dict(kind="batched", pH=30, nS=12, nI=4, B=4096, seed=2024),
+    # ONE problem of config 4's size (what a single controller solves per period): the one-cluster kernel, latency only
+    "c4s": dict(kind="single", N=480, M=120, seed=12347),
     # BASELINE config 5: 2^20 independent MPC problems in total, sharded contiguously over the ranks (strong scaling)
     "c5": dict(kind="batched", pH=30, nS=12, nI=4, B_total=1 << 20, seed=2025),
 }
@@ -600,6 +604,7 @@ def run_ours(args, rank, world, local_rank):
         top["setup"] = top["single"].pop("setup", None)
         top["batched_c4"] = batched_leg(ctx, "c4", sampler=None, cpu=False, parity=cpu)
         top["onchip"] = single_leg(ctx, "c2", sampler=None, cpu=False, parity=False, setup=False)
+        top["one_mpc_sized_problem"] = single_leg(ctx, "c4s", sampler=None, cpu=False, parity=False, setup=False)
     if ctx.dist is not None:
         ctx.dist.barrier()
         ctx.dist.destroy_process_group()

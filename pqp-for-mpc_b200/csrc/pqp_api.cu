@@ -777,6 +777,14 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		*y_res = h->ybuf1;
 		return PQP_OK;
 	}
+	if (pqp_gemv_cluster_supported(N)) {
+		/* a mid-size problem (one condensed-MPC QP): one thread-block cluster, y exchanged through distributed shared memory */
+		h->last_kernel = iters > 0 ? "gemv_cluster" : "gemv_cluster_tol";
+		CK(pqp_launch_gemv_cluster(&a, h->stream));
+		h->launches++;
+		*y_res = h->ybuf1;
+		return PQP_OK;
+	}
 	if (h->gemv_grid <= 0) return PQP_ERR_UNSUPPORTED;
 	if (h->small_ok && !(iters <= 0 && pqp_env("PQP_GEMV_SMALL_TOL") && atoi(pqp_env("PQP_GEMV_SMALL_TOL")) == 0)) {
 		/* fixed count, or run to tolerance with the stop test evaluated in the kernel every check_every updates */

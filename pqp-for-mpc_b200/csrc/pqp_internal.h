@@ -112,6 +112,10 @@ cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident
 /* one-CTA variant for N <= 128 (pqp_gemv_cta.cu): fixed count or run to tolerance; result left in ybuf1, status written */
 int pqp_gemv_cta_supported(int N);
 cudaError_t pqp_launch_gemv_cta(const pqp_gemv_args *a, cudaStream_t s);
+/* one-cluster variant for 128 < N <= 768 (pqp_gemv_cluster.cu): 16 (or 8) CTAs, y exchanged through distributed shared memory; fixed
+ * count or run to tolerance; result left in ybuf1, status written */
+int pqp_gemv_cluster_supported(int N);
+cudaError_t pqp_launch_gemv_cluster(const pqp_gemv_args *a, cudaStream_t s);
 /* register-resident variant for small N (pqp_gemv_small.cu); result left in ybuf1 */
 int pqp_gemv_small_plan(int N, int ldq, int grid, int *wpr, int *cpt);
 cudaError_t pqp_launch_gemv_small(const pqp_gemv_args *a, int wpr, int cpt, void *pk0, void *pk1, cudaStream_t s);
