@@ -100,6 +100,7 @@ struct pqp_handle {
 	int gemv_grid, gemv_resident;
 	int tma_ok, tma_stages, tma_resident, tma_yc, tma_pinned;
 	int small_ok, small_wpr, small_cpt, small_grid;
+	int cluster_state; /* one-cluster kernel for this handle: 0 not decided, 1 use it, -1 the multi-CTA kernel was faster here */
 	int sym_state; /* 0 not examined, 1 Qd symmetric and the unit array built, -1 unavailable */
 	pqp_sym_plan sym;
 	int l2_window_set;
@@ -777,7 +778,42 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		*y_res = h->ybuf1;
 		return PQP_OK;
 	}
-	if (pqp_gemv_cluster_supported(N)) {
+	if (pqp_gemv_cluster_supported(N) && h->cluster_state == 0) {
+		/* Decided once per handle by a measurement, not by a table: 64 updates on each kernel (CUDA events; y is set up again before
+		 * every launch, so the trial leaves nothing behind).  On the B200s measured the cluster wins below N = 512 by 1.1-1.6x, but its
+		 * speed rests on SM-to-SM latency inside one GPC, which the floorsweeping of an individual part may change; a box where the
+		 * multi-CTA kernel is faster keeps it.  PQP_GEMV_CLUSTER=1 skips the trial, =0 never uses the cluster. */
+		const char *e = pqp_env("PQP_GEMV_CLUSTER");
+		h->cluster_state = 1;
+		if (!(e && atoi(e) == 1) && h->small_ok && h->gemv_grid > 0) {
+			pqp_gemv_args ta = a;
+			float ms_cluster = 0.0f, ms_small = 0.0f;
+			ta.iters = 64;
+			ta.status = h->st; /* scratch: the real solve writes it again */
+			for (int rep = 0; rep < 2; rep++) { /* the first pair warms both kernels up */
+				CK(cudaEventRecord(h->ev0, h->stream));
+				CK(pqp_launch_gemv_cluster(&ta, h->stream));
+				CK(cudaEventRecord(h->ev1, h->stream));
+				CK(cudaEventSynchronize(h->ev1));
+				CK(cudaEventElapsedTime(&ms_cluster, h->ev0, h->ev1));
+				pqp_gemv_args tb = ta;
+				tb.grid = h->small_grid;
+				CK(cudaEventRecord(h->ev0, h->stream));
+				CK(pqp_launch_gemv_small(&tb, h->small_wpr, h->small_cpt, h->pk0, h->pk1, h->stream));
+				CK(cudaEventRecord(h->ev1, h->stream));
+				CK(cudaEventSynchronize(h->ev1));
+				CK(cudaEventElapsedTime(&ms_small, h->ev0, h->ev1));
+				h->launches += 2;
+			}
+			if (ms_small < ms_cluster) h->cluster_state = -1;
+			if (pqp_env("PQP_VERBOSE"))
+				fprintf(stderr, "pqp: one-cluster kernel %.1f us, multi-CTA kernel %.1f us per 64 updates at N=%d: using the %s\n", 1e3 * ms_cluster,
+					1e3 * ms_small, N, h->cluster_state == 1 ? "cluster" : "multi-CTA kernel");
+			/* the trials read the caller's y_0 and wrote ybuf1; the launchers reset their own exchange state */
+			CK(cudaMemsetAsync(h->ybuf1, 0, (size_t)ldq * sizeof(float), h->stream));
+		}
+	}
+	if (pqp_gemv_cluster_supported(N) && h->cluster_state == 1) {
 		/* a mid-size problem (one condensed-MPC QP): one thread-block cluster, y exchanged through distributed shared memory */
 		h->last_kernel = iters > 0 ? "gemv_cluster" : "gemv_cluster_tol";
 		CK(pqp_launch_gemv_cluster(&a, h->stream));
