@@ -770,14 +770,6 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		return PQP_OK;
 	}
 
-	if (pqp_gemv_cta_supported(N) && !(pqp_env("PQP_GEMV_CTA") && atoi(pqp_env("PQP_GEMV_CTA")) == 0)) {
-		/* a problem that fits one thread block: no exchange through L2 at all */
-		h->last_kernel = iters > 0 ? "gemv_cta" : "gemv_cta_tol";
-		CK(pqp_launch_gemv_cta(&a, h->stream));
-		h->launches++;
-		*y_res = h->ybuf1;
-		return PQP_OK;
-	}
 	if (pqp_gemv_cluster_supported(N) && h->cluster_state == 0) {
 		/* Decided once per handle by a measurement, not by a table: 64 updates on each kernel (CUDA events; y is set up again before
 		 * every launch, so the trial leaves nothing behind).  On the B200s measured the cluster wins below N = 512 by 1.1-1.6x, but its
@@ -785,7 +777,8 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		 * multi-CTA kernel is faster keeps it.  PQP_GEMV_CLUSTER=1 skips the trial, =0 never uses the cluster. */
 		const char *e = pqp_env("PQP_GEMV_CLUSTER");
 		h->cluster_state = 1;
-		if (!(e && atoi(e) == 1) && h->small_ok && h->gemv_grid > 0) {
+		const int cta_alt = pqp_gemv_cta_supported(N) && !(pqp_env("PQP_GEMV_CTA") && atoi(pqp_env("PQP_GEMV_CTA")) == 0);
+		if (!(e && atoi(e) == 1) && (cta_alt || (h->small_ok && h->gemv_grid > 0))) {
 			pqp_gemv_args ta = a;
 			float ms_cluster = 0.0f, ms_small = 0.0f;
 			ta.iters = 64;
@@ -799,7 +792,8 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 				pqp_gemv_args tb = ta;
 				tb.grid = h->small_grid;
 				CK(cudaEventRecord(h->ev0, h->stream));
-				CK(pqp_launch_gemv_small(&tb, h->small_wpr, h->small_cpt, h->pk0, h->pk1, h->stream));
+				if (cta_alt) CK(pqp_launch_gemv_cta(&tb, h->stream));
+				else CK(pqp_launch_gemv_small(&tb, h->small_wpr, h->small_cpt, h->pk0, h->pk1, h->stream));
 				CK(cudaEventRecord(h->ev1, h->stream));
 				CK(cudaEventSynchronize(h->ev1));
 				CK(cudaEventElapsedTime(&ms_small, h->ev0, h->ev1));
@@ -807,8 +801,8 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 			}
 			if (ms_small < ms_cluster) h->cluster_state = -1;
 			if (pqp_env("PQP_VERBOSE"))
-				fprintf(stderr, "pqp: one-cluster kernel %.1f us, multi-CTA kernel %.1f us per 64 updates at N=%d: using the %s\n", 1e3 * ms_cluster,
-					1e3 * ms_small, N, h->cluster_state == 1 ? "cluster" : "multi-CTA kernel");
+				fprintf(stderr, "pqp: one-cluster kernel %.1f us, the alternative %.1f us per 64 updates at N=%d: using the %s\n", 1e3 * ms_cluster,
+					1e3 * ms_small, N, h->cluster_state == 1 ? "cluster" : "alternative");
 			/* the trials read the caller's y_0 and wrote ybuf1; the launchers reset their own exchange state */
 			CK(cudaMemsetAsync(h->ybuf1, 0, (size_t)ldq * sizeof(float), h->stream));
 		}
@@ -817,6 +811,14 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		/* a mid-size problem (one condensed-MPC QP): one thread-block cluster, y exchanged through distributed shared memory */
 		h->last_kernel = iters > 0 ? "gemv_cluster" : "gemv_cluster_tol";
 		CK(pqp_launch_gemv_cluster(&a, h->stream));
+		h->launches++;
+		*y_res = h->ybuf1;
+		return PQP_OK;
+	}
+	if (pqp_gemv_cta_supported(N) && !(pqp_env("PQP_GEMV_CTA") && atoi(pqp_env("PQP_GEMV_CTA")) == 0)) {
+		/* a problem that fits one thread block: no exchange through L2 at all */
+		h->last_kernel = iters > 0 ? "gemv_cta" : "gemv_cta_tol";
+		CK(pqp_launch_gemv_cta(&a, h->stream));
 		h->launches++;
 		*y_res = h->ybuf1;
 		return PQP_OK;

@@ -1,9 +1,9 @@
 /*
- * pqp_gemv_cluster.cu -- the PQP loop of ONE mid-size problem (128 < N <= 512: a single condensed-MPC QP, config C4's shape as one
+ * pqp_gemv_cluster.cu -- the PQP loop of ONE mid-size problem (64 < N <= 512: a single condensed-MPC QP, config C4's shape as one
  * problem) on ONE thread-block cluster, y exchanged through distributed shared memory.  sm_100a.
  *
  * The multi-CTA kernels (pqp_gemv_small.cu) pay two L2 round trips per update for the exchange of y: ~1.0 us per update from N = 128
- * to N = 512 whatever the arithmetic.  A problem of this size fits the registers of 16 SMs, and 16 SMs are one cluster (non-portable
+ * to N = 512 whatever the arithmetic (and the one-block kernel slows to 1.0-1.25 us above N = 64).  A problem of this size fits the registers of 16 SMs, and 16 SMs are one cluster (non-portable
  * size; 8 where that is refused): solveQuadraticDual's loop (PQP_CPU.c:718-740) then never leaves the cluster.
  *   - CTA c of the cluster owns rows [cR, cR + R), R = ceil(N / CS); warp w of its 16 takes rows w and w + 16 of them, lane l the
  *     float4 column groups l, l + 32, ... -- the whole matrix sits in registers for the solve, already split into max(q,0) /
@@ -388,14 +388,16 @@ int gc_probe(void)
 
 } /* namespace */
 
-/* 128 < N: below that one thread block does it without any exchange (pqp_gemv_cta.cu).  Up to 32 rows per CTA (two per warp) and 512
+/* 64 < N: up to there one thread block does it without any exchange in 0.18-0.30 us per update (pqp_gemv_cta.cu; measured 0.97 at
+ * N = 96 and 1.25 at N = 128, against 0.52 here).  Up to 32 rows per CTA (two per warp) and 512
  * padded columns, i.e. N <= 512 on a cluster of 16: beyond that the 16 SMs' arithmetic costs more than the exchange saves (measured:
  * N = 144..256 0.60 us per update against 0.95-1.00 for the multi-CTA kernel, N = 480 0.94 against 1.05, N = 640 slower). */
 int pqp_gemv_cluster_supported(int N)
 {
 	const char *e = pqp_env("PQP_GEMV_CLUSTER");
 	if (e && atoi(e) == 0) return 0;
-	if (N <= 128) return 0;
+	const char *m = pqp_env("PQP_GEMV_CLUSTER_MIN"); /* experiments: the largest N the cluster leaves alone */
+	if (N <= (m ? atoi(m) : 64)) return 0;
 	const int cs = gc_probe();
 	if (cs == 0) return 0;
 	int R, Rpad, RW, U;

@@ -447,12 +447,13 @@ def test_single_update_from_the_dense_split_operands(pqp, oracle32):
             assert np.array_equal(Y1[0], want)
 
 
-def test_one_block_kernel_small_problems(pqp, oracle32, oracle64, gold_example):
+def test_one_block_kernel_small_problems(pqp, oracle32, oracle64, gold_example, monkeypatch):
     """N <= 128 runs in ONE thread block (pqp_gemv_cta.cu): the shipped example and every size class of that kernel, fixed
     count against the oracle (FAST tolerance rule), status block against the same quantities formed in float64, run to
     tolerance bit-identical to the fixed-count solve at the reported count, and the cap."""
     rng = np.random.default_rng(12)
     g = gold_example
+    monkeypatch.setenv("PQP_GEMV_CLUSTER", "0")  # above N = 64 a handle would otherwise try the one-cluster kernel: this test is of the one-block kernel
     cases = [(g["Qd"], g["Fd"], 312)]
     for N in (1, 5, 32, 33, 64, 65, 100, 128):
         A = rng.standard_normal((N, max(1, (3 * N) // 2))).astype(np.float32)
@@ -503,7 +504,7 @@ def test_one_block_kernel_small_problems(pqp, oracle32, oracle64, gold_example):
 
 
 def test_one_cluster_kernel_mid_size_problems(pqp, oracle32, oracle64):
-    """128 < N <= 512 runs on ONE thread-block cluster with y exchanged through distributed shared memory (pqp_gemv_cluster.cu):
+    """64 < N <= 512 runs on ONE thread-block cluster with y exchanged through distributed shared memory (pqp_gemv_cluster.cu):
     every shape class of that kernel (one / two rows per warp, 1-4 column groups, a last CTA with few or no rows, N not a multiple
     of 4), fixed count against the oracle (FAST tolerance rule), status block against the same quantities formed in float64,
     bit-reproducible, run to tolerance bit-identical to the fixed-count solve at the reported count, the cap, and the multi-CTA
@@ -513,7 +514,7 @@ def test_one_cluster_kernel_mid_size_problems(pqp, oracle32, oracle64):
     # is of THIS kernel, whatever the box would choose
     os.environ["PQP_GEMV_CLUSTER"] = "1"
     try:
-        for N in (129, 130, 144, 255, 256, 300, 385, 480, 511, 512):
+        for N in (65, 100, 128, 129, 130, 144, 255, 256, 300, 385, 480, 511, 512):
             A = rng.standard_normal((N, (3 * N) // 2)).astype(np.float32)
             Qd, Fd, K = (A @ A.T).astype(np.float32), rng.uniform(-50, 50, N).astype(np.float32), 60
             y32, _ = oracle32.solve_fixed(Qd, Fd, K)
