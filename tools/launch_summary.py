@@ -11,7 +11,7 @@ hdr = rows[0]
 kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
 tot, cnt = defaultdict(float), defaultdict(int)
 for r in rows[1:]:
-    name = re.sub(r"\(.*", "", r[kn])
+    name = re.sub(r"\(.*", "", r[kn].replace("(anonymous namespace)::", "").replace("<unnamed>::", ""))
     name = re.sub(r"<.*", "", name)
     v = float(r[mv].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[mu], 1e-3)
     tot[name] += v
