@@ -972,10 +972,14 @@ enum { FUSE_REFRESH = 1, FUSE_RECOVER = 2 };
  * Needs: a batch, fixed count, FAST order, the int8 engine, a Qd with the +/- row-pair structure, the handle's own Fp model,
  * no state-dependent constraint offsets (Kx / Kd: the separate kernels keep those), room for the scratch in the operand ring.
  */
+/* Batches up to this size go to one thread-block cluster per problem when the size allows (pqp_gemv_cluster.cu; four 16-SM clusters run
+ * at a time on a B200, measured at N = 480 per 1000 updates: B = 4 1.0 ms, 8 2.4-2.6, 16 4.2-5.2, 18 5.2-6.4); above, the tensor-core
+ * kernels' 8.7 ms for any batch up to 4096 is the shorter or as short. */
+#define PQP_CLUSTER_BATCH_MAX 16
 static int fused_path(pqp_handle *h, int B, int iters)
 {
 	const char *e;
-	if (B <= 32 || h->o.order == PQP_ORDER_STRICT || !h->have_fp_model || h->Kx || h->Kd || (iters > 0 && h->o.accelerate > 0)) return 0;
+	if (B <= PQP_CLUSTER_BATCH_MAX || h->o.order == PQP_ORDER_STRICT || !h->have_fp_model || h->Kx || h->Kd || (iters > 0 && h->o.accelerate > 0)) return 0;
 	if (iters <= 0 && pqp_env("PQP_IMMA_PAIRED_TOL") && atoi(pqp_env("PQP_IMMA_PAIRED_TOL")) == 0) return 0;
 	if ((e = pqp_env("PQP_IMMA_FUSE")) && atoi(e) == 0) return 0;
 	if ((e = pqp_env("PQP_IMMA_PAIR")) && atoi(e) == 0) return 0;
@@ -1085,7 +1089,7 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 	/* fixed count: any batched engine; run-to-tolerance (iters <= 0): the int8 engine evaluates the stop test per problem itself */
 	const int batched = B > 1 && !strict &&
 			    (iters > 0 ? (engine != BATCH_SIMT || pqp_batched_simt_supported(N)) : engine == BATCH_IMMA);
-	if (iters <= 0 && B > 32 && !strict && engine == BATCH_IMMA && pqp_batched_imma_pair_supported(N) &&
+	if (iters <= 0 && B > PQP_CLUSTER_BATCH_MAX && !strict && engine == BATCH_IMMA && pqp_batched_imma_pair_supported(N) &&
 	    !(pqp_env("PQP_IMMA_PAIR") && atoi(pqp_env("PQP_IMMA_PAIR")) == 0) && !(pqp_env("PQP_IMMA_PAIRED_TOL") && atoi(pqp_env("PQP_IMMA_PAIRED_TOL")) == 0)) {
 		int rc = ensure_imma_paired(h);
 		if (rc) return rc;
@@ -1119,6 +1123,29 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, h->Md, h->Kp, h->o.erc, h->o.eac, B, iters + h->iters_base, NULL, h->stream));
 			h->launches += 2;
 		}
+	} else if (B > 1 && B <= PQP_CLUSTER_BATCH_MAX && !strict && h->o.accelerate <= 0 && !pqp_env("PQP_BATCHED") && pqp_gemv_cluster_supported(N)) {
+		/* A handful of problems of a single controller's size: one thread-block cluster each (pqp_gemv_cluster.cu), as many at a time as
+		 * the device has GPCs.  The tensor-core kernels pay the latency of a 64-problem tile whatever B is (8.7 ms per 1000 updates at
+		 * N = 480; the single-CTA kernel that used to serve B <= 32: 21 ms); four clusters at a time finish four problems per 1.0 ms. */
+		if (Y0) {
+			if (Y0 != h->Y) CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+		} else {
+			CK(pqp_launch_fill(h->Y, h->o.y_init, (size_t)B * N, h->stream));
+			h->launches++;
+		}
+		pqp_gemv_args a;
+		memset(&a, 0, sizeof a);
+		a.Q = h->Q; a.ldq = h->ldq; a.N = N; a.theta = h->theta; a.Fd = h->Fd; a.Kp = h->Kp; a.Md = Md;
+		a.ybuf0 = h->Y; a.ybuf1 = h->Y; /* in place: every CTA reads y_0 before the cluster's first barrier and writes its rows after the loop */
+		a.iters = iters; a.max_iters = h->o.max_iters; a.check_every = h->o.check_every;
+		a.erc = h->o.erc; a.eac = h->o.eac; a.eaj = h->o.eaj; a.erj = h->o.erj;
+		a.status = h->st; a.result_buf = h->result_buf;
+		CK(cudaEventRecord(h->ev0, h->stream));
+		CK(pqp_launch_gemv_cluster_batch(&a, B, N, N, h->stream));
+		CK(cudaEventRecord(h->ev1, h->stream));
+		h->ev_valid = 1;
+		h->launches++;
+		h->last_kernel = iters > 0 ? "gemv_cluster_batch" : "gemv_cluster_batch_tol";
 	} else if (batched) {
 		int rc = engine == BATCH_IMMA ? ensure_imma_tiles(h) : (engine == BATCH_UMMA ? ensure_umma_tiles(h) : ensure_batched_operands(h));
 		if (rc) return rc;
@@ -1139,7 +1166,7 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != 8 && cluster != 16) cluster = 1;
 			/* fixed count, more than one 32-problem tile, at least two M tiles: the CTA-pair kernel (64 problems per pair, rows of Q
 			 * split over the two SMs) moves half the operand bytes per problem through shared memory */
-			const int pair = iters > 0 && B > 32 && pqp_batched_imma_pair_supported(N) &&
+			const int pair = iters > 0 && B > PQP_CLUSTER_BATCH_MAX && pqp_batched_imma_pair_supported(N) &&
 					 (pqp_env("PQP_IMMA_PAIR") ? atoi(pqp_env("PQP_IMMA_PAIR")) != 0 : 1);
 			if (pair) {
 				/* a Qd with the +/- row-pair structure of a box-constrained MPC dual: half the tensor work (PAIRED instantiation) */

@@ -78,8 +78,19 @@ __device__ __forceinline__ void gc_spin(unsigned &n)
 	if (++n > (1u << 28)) __trap();
 }
 
-template <int RW, int U, bool TOL> __global__ void __launch_bounds__(GC_THREADS, 1) gemv_cluster_kernel(const pqp_gemv_args a, int R, int Rpad)
+template <int RW, int U, bool TOL> __global__ void __launch_bounds__(GC_THREADS, 1) gemv_cluster_kernel(const pqp_gemv_args a0, int R, int Rpad, int fd_stride,
+												     int y_stride)
 {
+	/* one cluster per problem: cluster b of the grid takes Fd, y, Md and the status block of problem b (strides 0: a single problem) */
+	pqp_gemv_args a = a0;
+	{
+		const int prob = (int)(blockIdx.x / gc_cluster_size());
+		a.Fd += (size_t)prob * fd_stride;
+		a.ybuf0 += (size_t)prob * y_stride;
+		a.ybuf1 += (size_t)prob * y_stride;
+		a.status += prob;
+		if (a.Md && fd_stride) a.Md += prob;
+	}
 	constexpr bool SPLIT = RW * U * 4 <= 32;
 	__shared__ __align__(128) GcSmem sm;
 	const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
@@ -405,11 +416,12 @@ int pqp_gemv_cluster_supported(int N)
 	return RW <= 2 && U <= 4 && cs * Rpad <= GC_MAXNP;
 }
 
-/* result left in ybuf1, status written by the kernel */
-cudaError_t pqp_launch_gemv_cluster(const pqp_gemv_args *a, cudaStream_t s)
+/* B problems sharing Q, one cluster each (B = 1: the single-problem call): Fd, y_0 (ybuf0), the result (ybuf1, may be ybuf0), Md and the
+ * status blocks of problem b at b * stride.  Clusters are independent; the device runs as many at a time as it has GPCs with 16 SMs. */
+cudaError_t pqp_launch_gemv_cluster_batch(const pqp_gemv_args *a, int B, int fd_stride, int y_stride, cudaStream_t s)
 {
 	const int cs = gc_probe();
-	if (cs == 0) return cudaErrorNotSupported;
+	if (cs == 0 || B < 1) return cudaErrorNotSupported;
 	int R, Rpad, RW, U;
 	gc_geometry(a->N, cs, &R, &Rpad, &RW, &U);
 	const void *fn = a->iters > 0 ? gc_fn<false>(RW, U) : gc_fn<true>(RW, U);
@@ -418,7 +430,7 @@ cudaError_t pqp_launch_gemv_cluster(const pqp_gemv_args *a, cudaStream_t s)
 	if (e != cudaSuccess) return e;
 	cudaLaunchConfig_t cfg;
 	memset(&cfg, 0, sizeof cfg);
-	cfg.gridDim = dim3(cs);
+	cfg.gridDim = dim3(cs * B);
 	cfg.blockDim = dim3(GC_THREADS);
 	cfg.stream = s;
 	cudaLaunchAttribute attr[1];
@@ -429,6 +441,9 @@ cudaError_t pqp_launch_gemv_cluster(const pqp_gemv_args *a, cudaStream_t s)
 	cfg.attrs = attr;
 	cfg.numAttrs = 1;
 	pqp_gemv_args args = *a;
-	void *params[] = { (void *)&args, (void *)&R, (void *)&Rpad };
+	void *params[] = { (void *)&args, (void *)&R, (void *)&Rpad, (void *)&fd_stride, (void *)&y_stride };
 	return cudaLaunchKernelExC(&cfg, fn, params);
 }
+
+/* result left in ybuf1, status written by the kernel */
+cudaError_t pqp_launch_gemv_cluster(const pqp_gemv_args *a, cudaStream_t s) { return pqp_launch_gemv_cluster_batch(a, 1, 0, 0, s); }

@@ -116,6 +116,8 @@ cudaError_t pqp_launch_gemv_cta(const pqp_gemv_args *a, cudaStream_t s);
  * count or run to tolerance; result left in ybuf1, status written */
 int pqp_gemv_cluster_supported(int N);
 cudaError_t pqp_launch_gemv_cluster(const pqp_gemv_args *a, cudaStream_t s);
+/* B problems sharing Q, one cluster each: Fd / ybuf0 / ybuf1 (may be the same array) / Md / status of problem b at b * stride */
+cudaError_t pqp_launch_gemv_cluster_batch(const pqp_gemv_args *a, int B, int fd_stride, int y_stride, cudaStream_t s);
 /* register-resident variant for small N (pqp_gemv_small.cu); result left in ybuf1 */
 int pqp_gemv_small_plan(int N, int ldq, int grid, int *wpr, int *cpt);
 cudaError_t pqp_launch_gemv_small(const pqp_gemv_args *a, int wpr, int cpt, void *pk0, void *pk1, cudaStream_t s);

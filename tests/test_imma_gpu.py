@@ -86,8 +86,17 @@ def test_imma_warm_start_and_chunking_are_exact(pqp):
         Yb, _, _ = s.solve(X, iters=30, Y0=Ya, status=False)
         Yc, _, _ = s.solve(X, iters=100, status=False)
         assert np.array_equal(Yb, Yc)
-        Yd, _, _ = s.solve(X[:17], iters=100, status=False)   # ragged tail, different CTA population
-        assert np.array_equal(Yd, Yc[:17])
+        Yd, _, _ = s.solve(X[:37], iters=100, status=False)   # ragged tail, different CTA population
+        assert np.array_equal(Yd, Yc[:37])
+        # up to 16 problems of this size run on one thread-block cluster each (plain fp32, the single-problem arithmetic): the same
+        # answers to rounding, and again independent of who else is in the batch
+        Ye, _, _ = s.solve(X[:13], iters=100, status=False)
+        assert s.last_kernel == "gemv_cluster_batch", s.last_kernel
+        assert np.abs(Ye - Yc[:13]).max() <= 2e-5 * np.abs(Yc[:13]).max()
+        Yf, _, _ = s.solve(X[:5], iters=100, status=False)
+        assert np.array_equal(Yf, Ye[:5])
+        Yg, _, _ = s.solve(X[:1], iters=100, status=False)
+        assert np.array_equal(Yg, Ye[:1])
 
 
 def test_c4_shape_against_oracle(pqp, oracle32, oracle64):

@@ -563,3 +563,45 @@ def test_one_cluster_kernel_mid_size_problems(pqp, oracle32, oracle64):
         assert np.array_equal(Ya, Y if s.last_kernel == "gemv_cluster" else Ym)
         Yb, _, _ = s.solve(Fd=Fd, iters=K)
         assert np.array_equal(Ya, Yb)
+
+
+def test_small_batches_run_one_cluster_per_problem(pqp, oracle32, oracle64, monkeypatch):
+    """2 <= B <= 16 problems of a single controller's size (64 < N <= 512) sharing one Hessian: one thread-block cluster per problem
+    (pqp_gemv_cluster.cu), the single-problem arithmetic -- every problem's duals, primal solution and status are those of the
+    one-problem call bit for bit, whoever else is in the batch, fixed count and run to tolerance; against the oracle with the
+    FAST rule; U bit-identical to computeUfromY on the GPU's y."""
+    from bench_problems import condensed_mpc
+    monkeypatch.setenv("PQP_GEMV_CLUSTER", "1")
+    prob, d, X = condensed_mpc(2024, 30, 12, 4, n_states=16, x_scale=150.0, min_violated=4)
+    K = 300
+    with pqp.Solver(d, prob, batch_capacity=16, eaj=1e-2, erj=1e-6, check_every=8, max_iters=6000) as s:
+        Y, U, st = s.solve(X, iters=K, primal=True)
+        assert s.last_kernel == "gemv_cluster_batch", s.last_kernel
+        Qd, th, _ = s.dual()
+        Fd, Fp = s.linear_terms(16)
+        for B in (2, 7, 9):
+            Yb, Ub, stb = s.solve(X[:B], iters=K, primal=True)
+            assert s.last_kernel == "gemv_cluster_batch"
+            assert np.array_equal(Yb, Y[:B]) and np.array_equal(Ub, U[:B]) and np.array_equal(stb["gap"], st["gap"][:B])
+        Y1, U1, st1 = s.solve(X[3:4], iters=K, primal=True)
+        assert s.last_kernel == "gemv_cluster" and np.array_equal(Y1[0], Y[3]) and np.array_equal(U1[0], U[3])
+        assert st1["gap"][0] == st["gap"][3] and st1["Jd"][0] == st["Jd"][3] and st["iters"][3] == K
+        for b in (0, 11, 15):
+            y32, _ = oracle32.solve_fixed(Qd, Fd[b], K)
+            y64, _ = oracle64.solve_fixed(Qd, Fd[b], K)
+            check_fast(Y[b], y32, y64, f"cluster batch, problem {b}")
+            assert np.array_equal(U[b], oracle32.recover_u(Y[b], Fp[b], prob["Gp"], prob["Qp_inv"]))
+        # run to tolerance: every cluster stops on its own; a problem's result is its fixed-count solve at its own count
+        Yt, Ut, stt = s.solve(X[:9], iters=0, primal=True)
+        assert s.last_kernel == "gemv_cluster_batch_tol"
+        assert np.all(stt["iters"] % 8 == 0) and len(set(stt["iters"].tolist())) > 1
+        for b in (0, 4, 8):
+            if stt["converged"][b]:
+                Yf, _, _ = s.solve(X[b:b + 1], iters=int(stt["iters"][b]))
+                assert np.array_equal(Yf[0], Yt[b]), b
+    # 17 problems and more: the tensor-core kernels
+    prob, d, X = condensed_mpc(2024, 30, 12, 4, n_states=17, x_scale=150.0, min_violated=4)
+    with pqp.Solver(d, prob, batch_capacity=17) as s:
+        Yp, _, _ = s.solve(X, iters=K, primal=True)
+        assert s.last_kernel == "batched_imma_paired"
+        assert np.abs(Yp[:16] - Y).max() <= 3e-5 * np.abs(Y).max()
