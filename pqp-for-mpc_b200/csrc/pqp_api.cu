@@ -1085,6 +1085,9 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 	const float *Md = ((want_status || iters <= 0) && h->have_fp_model) ? h->Md : NULL; /* tolerance mode needs Jd, hence Md */
 	h->ev_valid = 0;
 
+	/* one block per problem (N <= 64), measured against the tensor-core kernel per 300 updates: N = 28 0.06 / 0.40 / 3.0 ms at B = 16 / 4096 /
+	 * 32768 against 1.3 / 1.0 / 7.2; N = 64 0.10 / 0.14 ms at B = 16 / 256 against 1.4 / 1.1, but 1.8 against 1.1 at B = 4096 */
+	const int cta_batch_max = pqp_env("PQP_CTA_BATCH_MAX") ? atoi(pqp_env("PQP_CTA_BATCH_MAX")) : (N <= 32 ? (1 << 30) : 2048);
 	const int engine = batched_engine(h);
 	/* fixed count: any batched engine; run-to-tolerance (iters <= 0): the int8 engine evaluates the stop test per problem itself */
 	const int batched = B > 1 && !strict &&
@@ -1123,6 +1126,28 @@ static int run_loop(pqp_handle *h, int B, int iters, const float *Y0, float *Y, 
 			CK(pqp_launch_status(h->st, h->Q, h->ldq, N, h->Y, N, h->Fd, h->Md, h->Kp, h->o.erc, h->o.eac, B, iters + h->iters_base, NULL, h->stream));
 			h->launches += 2;
 		}
+	} else if (B > 1 && B <= cta_batch_max && N <= 64 && !strict && h->o.accelerate <= 0 && !pqp_env("PQP_BATCHED") && pqp_gemv_cta_supported(N) &&
+		   !(pqp_env("PQP_GEMV_CTA") && atoi(pqp_env("PQP_GEMV_CTA")) == 0)) {
+		/* Problems that fit one thread block (pqp_gemv_cta.cu), any number of them: one block each, many blocks per SM */
+		if (Y0) {
+			if (Y0 != h->Y) CK(cudaMemcpyAsync(h->Y, Y0, (size_t)B * N * sizeof(float), cudaMemcpyDefault, h->stream));
+		} else {
+			CK(pqp_launch_fill(h->Y, h->o.y_init, (size_t)B * N, h->stream));
+			h->launches++;
+		}
+		pqp_gemv_args a;
+		memset(&a, 0, sizeof a);
+		a.Q = h->Q; a.ldq = h->ldq; a.N = N; a.theta = h->theta; a.Fd = h->Fd; a.Kp = h->Kp; a.Md = Md;
+		a.ybuf0 = h->Y; a.ybuf1 = h->Y; /* in place: a block reads all of its y_0 before it writes */
+		a.iters = iters; a.max_iters = h->o.max_iters; a.check_every = h->o.check_every;
+		a.erc = h->o.erc; a.eac = h->o.eac; a.eaj = h->o.eaj; a.erj = h->o.erj;
+		a.status = h->st; a.result_buf = h->result_buf;
+		CK(cudaEventRecord(h->ev0, h->stream));
+		CK(pqp_launch_gemv_cta_batch(&a, B, N, N, h->stream));
+		CK(cudaEventRecord(h->ev1, h->stream));
+		h->ev_valid = 1;
+		h->launches++;
+		h->last_kernel = iters > 0 ? "gemv_cta_batch" : "gemv_cta_batch_tol";
 	} else if (B > 1 && B <= PQP_CLUSTER_BATCH_MAX && !strict && h->o.accelerate <= 0 && !pqp_env("PQP_BATCHED") && pqp_gemv_cluster_supported(N)) {
 		/* A handful of problems of a single controller's size: one thread-block cluster each (pqp_gemv_cluster.cu), as many at a time as
 		 * the device has GPCs.  The tensor-core kernels pay the latency of a 64-problem tile whatever B is (8.7 ms per 1000 updates at

@@ -14,8 +14,15 @@
 #define CT_TPR 4     /* threads per row */
 #define CT_MAXN 128
 
-template <int CPT, bool TOL> __global__ void __launch_bounds__(CT_TPR *CT_MAXN, 1) gemv_cta_kernel(const pqp_gemv_args a)
+template <int CPT, bool TOL> __global__ void __launch_bounds__(CT_TPR *CT_MAXN, 1) gemv_cta_kernel(const pqp_gemv_args a0, int fd_stride, int y_stride)
 {
+	/* one block per problem: block b takes Fd, y, Md and the status block of problem b (strides 0: a single problem) */
+	pqp_gemv_args a = a0;
+	a.Fd += (size_t)blockIdx.x * fd_stride;
+	a.ybuf0 += (size_t)blockIdx.x * y_stride;
+	a.ybuf1 += (size_t)blockIdx.x * y_stride;
+	a.status += blockIdx.x;
+	if (a.Md && fd_stride) a.Md += blockIdx.x;
 	__shared__ float ys[2][CT_MAXN + 32];
 	__shared__ float red[16][8];
 	__shared__ int stop_s;
@@ -143,8 +150,9 @@ template <bool TOL> static const void *cta_fn(int cpt)
 	}
 }
 
-/* result left in ybuf1, status written by the kernel */
-cudaError_t pqp_launch_gemv_cta(const pqp_gemv_args *a, cudaStream_t s)
+/* B problems sharing Q, one block each (B = 1: the single-problem call): Fd, y_0 (ybuf0), the result (ybuf1, may be ybuf0: a block reads
+ * all of its y_0 before it writes), Md and the status blocks of problem b at b * stride */
+cudaError_t pqp_launch_gemv_cta_batch(const pqp_gemv_args *a, int B, int fd_stride, int y_stride, cudaStream_t s)
 {
 	const int N = a->N;
 	const int cpt = N <= 32 ? 8 : (N <= 64 ? 16 : 32);
@@ -152,6 +160,9 @@ cudaError_t pqp_launch_gemv_cta(const pqp_gemv_args *a, cudaStream_t s)
 	int threads = (CT_TPR * N + 31) / 32 * 32;
 	if (threads < 32) threads = 32;
 	pqp_gemv_args args = *a;
-	void *params[] = { (void *)&args };
-	return cudaLaunchKernel(fn, dim3(1), dim3(threads), params, 0, s);
+	void *params[] = { (void *)&args, (void *)&fd_stride, (void *)&y_stride };
+	return cudaLaunchKernel(fn, dim3(B), dim3(threads), params, 0, s);
 }
+
+/* result left in ybuf1, status written by the kernel */
+cudaError_t pqp_launch_gemv_cta(const pqp_gemv_args *a, cudaStream_t s) { return pqp_launch_gemv_cta_batch(a, 1, 0, 0, s); }

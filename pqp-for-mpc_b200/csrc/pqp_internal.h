@@ -112,6 +112,8 @@ cudaError_t pqp_launch_gemv_tma(const pqp_gemv_args *a, int stages, int resident
 /* one-CTA variant for N <= 128 (pqp_gemv_cta.cu): fixed count or run to tolerance; result left in ybuf1, status written */
 int pqp_gemv_cta_supported(int N);
 cudaError_t pqp_launch_gemv_cta(const pqp_gemv_args *a, cudaStream_t s);
+/* B problems sharing Q, one block each: Fd / ybuf0 / ybuf1 (may be the same array) / Md / status of problem b at b * stride */
+cudaError_t pqp_launch_gemv_cta_batch(const pqp_gemv_args *a, int B, int fd_stride, int y_stride, cudaStream_t s);
 /* one-cluster variant for 128 < N <= 768 (pqp_gemv_cluster.cu): 16 (or 8) CTAs, y exchanged through distributed shared memory; fixed
  * count or run to tolerance; result left in ybuf1, status written */
 int pqp_gemv_cluster_supported(int N);

@@ -17,6 +17,13 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
+@pytest.fixture(autouse=True)
+def _tensor_core_kernels_for_tiny_problems(monkeypatch):
+    """Batches of problems that fit one thread block (N <= 64) are served by one block per problem; this file is about the
+    tensor-core kernels, also on the tiny shapes that make good edge cases for them."""
+    monkeypatch.setenv("PQP_CTA_BATCH_MAX", "0")
+
+
 def _mpc(seed, pH, nS, nI, B):
     from bench_problems import condensed_mpc
     return condensed_mpc(seed, pH, nS, nI, n_states=B)

@@ -241,7 +241,7 @@ def test_batched_matches_oracle_per_problem(pqp, oracle32, oracle64):
     X = X[:B]
     with pqp.Solver(d, prob) as s:
         Y, U, st = s.solve(X, iters=K, primal=True)
-        assert s.last_kernel.startswith("batched")
+        assert s.last_kernel.startswith("batched") or s.last_kernel == "gemv_cta_batch"   # N = 48: one thread block per problem
         Qd, th, GQ = s.dual()
         for b in range(B):
             Fp = oracle32.compute_fp(prob["Fp1"], prob["Fp2"], prob["Fp3"], prob["D"], X[b])
@@ -605,3 +605,35 @@ def test_small_batches_run_one_cluster_per_problem(pqp, oracle32, oracle64, monk
         Yp, _, _ = s.solve(X, iters=K, primal=True)
         assert s.last_kernel == "batched_imma_paired"
         assert np.abs(Yp[:16] - Y).max() <= 3e-5 * np.abs(Y).max()
+
+
+def test_batches_of_problems_that_fit_one_block(pqp, oracle32, oracle64):
+    """B problems with N <= 64 sharing one Hessian (the shipped example's size class): one thread block per problem
+    (pqp_gemv_cta.cu), many blocks per SM.  Every problem's duals, primal solution and status equal the one-problem call bit for
+    bit, whoever else is in the batch; fixed count against the oracle (FAST rule); run to tolerance: every block stops on its own."""
+    from bench_problems import condensed_mpc
+    for pH, nI, B in ((7, 1, 300), (8, 2, 70)):
+        prob, d, X = condensed_mpc(5, pH, 4, nI, n_states=B, x_scale=20.0)
+        K = 200
+        with pqp.Solver(d, prob, batch_capacity=B, eaj=1e-3, erj=1e-6, check_every=8, max_iters=20000) as s:
+            Y, U, st = s.solve(X, iters=K, primal=True)
+            assert s.last_kernel == "gemv_cta_batch", s.last_kernel
+            Qd, th, _ = s.dual()
+            Fd, Fp = s.linear_terms(B)
+            Yb, Ub, stb = s.solve(X[:9], iters=K, primal=True)
+            assert np.array_equal(Yb, Y[:9]) and np.array_equal(Ub, U[:9]) and np.array_equal(stb["gap"], st["gap"][:9])
+            Y1, U1, st1 = s.solve(X[5:6], iters=K, primal=True)
+            assert s.last_kernel == "gemv_cta" and np.array_equal(Y1[0], Y[5]) and st1["gap"][0] == st["gap"][5] and st["iters"][5] == K
+            for b in (0, B // 2, B - 1):
+                y32, _ = oracle32.solve_fixed(Qd, Fd[b], K)
+                y64, _ = oracle64.solve_fixed(Qd, Fd[b], K)
+                if np.isfinite(y32).all():
+                    check_fast(Y[b], y32, y64, f"one block per problem, N={d.N}, problem {b}")
+                    assert np.array_equal(U[b], oracle32.recover_u(Y[b], Fp[b], prob["Gp"], prob["Qp_inv"]))
+            Yt, _, stt = s.solve(X, iters=0, primal=True)
+            assert s.last_kernel == "gemv_cta_batch_tol"
+            conv = stt["converged"] == 1
+            assert conv.mean() > 0.9 and np.all(stt["iters"][conv] % 8 == 0) and len(set(stt["iters"][conv].tolist())) > 1
+            for b in np.flatnonzero(conv)[:3]:
+                Yf, _, _ = s.solve(X[b:b + 1], iters=int(stt["iters"][b]))
+                assert np.array_equal(Yf[0], Yt[b]), b
