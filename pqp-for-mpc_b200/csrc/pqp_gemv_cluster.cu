@@ -34,6 +34,9 @@
 #define GC_THREADS 512
 #define GC_WARPS 16
 #define GC_MAXCS 16
+#ifndef GC_SMALL_N
+#define GC_SMALL_N 0 /* problems up to this size take a cluster of 8 (0: always the largest cluster) */
+#endif
 #define GC_MAXNP 512 /* padded length of y: 4 column groups of 128 */
 
 namespace {
@@ -397,6 +400,17 @@ int gc_probe(void)
 	return gc_max_cluster;
 }
 
+/* cluster size for a problem of N duals: the largest the device schedules, but 8 where 8 CTAs hold the matrix as comfortably (N <= 256:
+ * at most two rows per warp either way) -- twice as many clusters then run at a time, which is what a small batch wants */
+int gc_size_for(int N)
+{
+	const int cs = gc_probe();
+	const char *e = pqp_env("PQP_CLUSTER_SIZE");
+	if (e && (atoi(e) == 8 || atoi(e) == 16) && atoi(e) <= cs) return atoi(e);
+	if (cs == 16 && N <= GC_SMALL_N) return 8;
+	return cs;
+}
+
 } /* namespace */
 
 /* 64 < N: up to there one thread block does it without any exchange in 0.18-0.30 us per update (pqp_gemv_cta.cu; measured 0.97 at
@@ -409,8 +423,8 @@ int pqp_gemv_cluster_supported(int N)
 	if (e && atoi(e) == 0) return 0;
 	const char *m = pqp_env("PQP_GEMV_CLUSTER_MIN"); /* experiments: the largest N the cluster leaves alone */
 	if (N <= (m ? atoi(m) : 64)) return 0;
-	const int cs = gc_probe();
-	if (cs == 0) return 0;
+	if (gc_probe() == 0) return 0;
+	const int cs = gc_size_for(N);
 	int R, Rpad, RW, U;
 	gc_geometry(N, cs, &R, &Rpad, &RW, &U);
 	return RW <= 2 && U <= 4 && cs * Rpad <= GC_MAXNP;
@@ -420,8 +434,8 @@ int pqp_gemv_cluster_supported(int N)
  * status blocks of problem b at b * stride.  Clusters are independent; the device runs as many at a time as it has GPCs with 16 SMs. */
 cudaError_t pqp_launch_gemv_cluster_batch(const pqp_gemv_args *a, int B, int fd_stride, int y_stride, cudaStream_t s)
 {
-	const int cs = gc_probe();
-	if (cs == 0 || B < 1) return cudaErrorNotSupported;
+	if (gc_probe() == 0 || B < 1) return cudaErrorNotSupported;
+	const int cs = gc_size_for(a->N);
 	int R, Rpad, RW, U;
 	gc_geometry(a->N, cs, &R, &Rpad, &RW, &U);
 	const void *fn = a->iters > 0 ? gc_fn<false>(RW, U) : gc_fn<true>(RW, U);
