@@ -799,9 +799,10 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 				CK(cudaEventElapsedTime(&ms_small, h->ev0, h->ev1));
 				h->launches += 2;
 			}
-			/* the cluster unless it is clearly slower here (its margin at N = 480 is 10 %: a plain comparison could flip from handle to
-			 * handle on noise, and with it the last bits of the results) */
-			if (1.25f * ms_small < ms_cluster) h->cluster_state = -1;
+			/* Hysteresis, so that the choice does not flip from handle to handle on noise (and with it the last bits of the results): up to
+			 * N = 320, where the cluster wins by 1.6x on most parts, it stays unless it is 1.25x slower here; above, where it wins by 10 %
+			 * at best and was measured 1.2-1.5x slower on the GPUs of one 8-GPU box, it has to be 5 % faster to be taken. */
+			if (N <= 320 ? (1.25f * ms_small < ms_cluster) : (1.05f * ms_cluster > ms_small)) h->cluster_state = -1;
 			if (pqp_env("PQP_VERBOSE"))
 				fprintf(stderr, "pqp: one-cluster kernel %.1f us, the alternative %.1f us per 64 updates at N=%d: using the %s\n", 1e3 * ms_cluster,
 					1e3 * ms_small, N, h->cluster_state == 1 ? "cluster" : "alternative");
