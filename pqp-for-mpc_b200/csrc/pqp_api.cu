@@ -771,8 +771,8 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 	}
 
 	if (pqp_gemv_cluster_supported(N) && h->cluster_state == 0) {
-		/* Decided once per handle by a measurement, not by a table: 64 updates on each kernel (CUDA events; y is set up again before
-		 * every launch, so the trial leaves nothing behind).  On the B200s measured the cluster wins below N = 512 by 1.1-1.6x, but its
+		/* Decided once per handle by a measurement, not by a table: each kernel at 32 and at 160 updates (CUDA events; y is set up again
+		 * before every launch, so the trial leaves nothing behind).  On the B200s measured the cluster wins below N = 512 by 1.1-1.6x, but its
 		 * speed rests on SM-to-SM latency inside one GPC, which the floorsweeping of an individual part may change; a box where the
 		 * multi-CTA kernel is faster keeps it.  PQP_GEMV_CLUSTER=1 skips the trial, =0 never uses the cluster. */
 		const char *e = pqp_env("PQP_GEMV_CLUSTER");
@@ -780,31 +780,36 @@ static int run_single(pqp_handle *h, const float *Fd, const float *Md, const flo
 		const int cta_alt = pqp_gemv_cta_supported(N) && !(pqp_env("PQP_GEMV_CTA") && atoi(pqp_env("PQP_GEMV_CTA")) == 0);
 		if (!(e && atoi(e) == 1) && (cta_alt || (h->small_ok && h->gemv_grid > 0))) {
 			pqp_gemv_args ta = a;
-			float ms_cluster = 0.0f, ms_small = 0.0f;
-			ta.iters = 64;
 			ta.status = h->st; /* scratch: the real solve writes it again */
-			for (int rep = 0; rep < 2; rep++) { /* the first pair warms both kernels up */
+			/* the cost of an UPDATE, not of a launch: the kernels differ in how they bring the matrix on chip, so each is timed at two
+			 * counts and the difference counts (rep 0 warms both up) */
+			float t_c[2] = { 0.0f, 0.0f }, t_s[2] = { 0.0f, 0.0f };
+			const int counts[2] = { 32, 160 };
+			for (int rep = 0; rep < 3; rep++) {
+				const int k = rep == 0 ? 0 : rep - 1;
+				pqp_gemv_args tb = ta;
+				tb.iters = counts[k];
 				CK(cudaEventRecord(h->ev0, h->stream));
-				CK(pqp_launch_gemv_cluster(&ta, h->stream));
+				CK(pqp_launch_gemv_cluster(&tb, h->stream));
 				CK(cudaEventRecord(h->ev1, h->stream));
 				CK(cudaEventSynchronize(h->ev1));
-				CK(cudaEventElapsedTime(&ms_cluster, h->ev0, h->ev1));
-				pqp_gemv_args tb = ta;
+				CK(cudaEventElapsedTime(&t_c[k], h->ev0, h->ev1));
 				tb.grid = h->small_grid;
 				CK(cudaEventRecord(h->ev0, h->stream));
 				if (cta_alt) CK(pqp_launch_gemv_cta(&tb, h->stream));
 				else CK(pqp_launch_gemv_small(&tb, h->small_wpr, h->small_cpt, h->pk0, h->pk1, h->stream));
 				CK(cudaEventRecord(h->ev1, h->stream));
 				CK(cudaEventSynchronize(h->ev1));
-				CK(cudaEventElapsedTime(&ms_small, h->ev0, h->ev1));
+				CK(cudaEventElapsedTime(&t_s[k], h->ev0, h->ev1));
 				h->launches += 2;
 			}
+			const float ms_cluster = fmaxf(t_c[1] - t_c[0], 1e-6f), ms_small = fmaxf(t_s[1] - t_s[0], 1e-6f); /* per 128 updates */
 			/* Hysteresis, so that the choice does not flip from handle to handle on noise (and with it the last bits of the results): up to
 			 * N = 320, where the cluster wins by 1.6x on most parts, it stays unless it is 1.25x slower here; above, where it wins by 10 %
 			 * at best and was measured 1.2-1.5x slower on the GPUs of one 8-GPU box, it has to be 5 % faster to be taken. */
 			if (N <= 320 ? (1.25f * ms_small < ms_cluster) : (1.05f * ms_cluster > ms_small)) h->cluster_state = -1;
 			if (pqp_env("PQP_VERBOSE"))
-				fprintf(stderr, "pqp: one-cluster kernel %.1f us, the alternative %.1f us per 64 updates at N=%d: using the %s\n", 1e3 * ms_cluster,
+				fprintf(stderr, "pqp: one-cluster kernel %.1f us, the alternative %.1f us per 128 updates at N=%d: using the %s\n", 1e3 * ms_cluster,
 					1e3 * ms_small, N, h->cluster_state == 1 ? "cluster" : "alternative");
 			/* the trials read the caller's y_0 and wrote ybuf1; the launchers reset their own exchange state */
 			CK(cudaMemsetAsync(h->ybuf1, 0, (size_t)ldq * sizeof(float), h->stream));

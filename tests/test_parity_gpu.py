@@ -510,7 +510,7 @@ def test_one_cluster_kernel_mid_size_problems(pqp, oracle32, oracle64):
     bit-reproducible, run to tolerance bit-identical to the fixed-count solve at the reported count, the cap, and the multi-CTA
     kernel still serving these sizes when asked to."""
     rng = np.random.default_rng(21)
-    # left alone, a handle times 64 updates on this kernel and on the multi-CTA one at its first solve and keeps the faster; the test
+    # left alone, a handle times this kernel and the multi-CTA one at its first solve and keeps the faster (with hysteresis); the test
     # is of THIS kernel, whatever the box would choose
     os.environ["PQP_GEMV_CLUSTER"] = "1"
     try:
