@@ -75,7 +75,7 @@ __device__ __forceinline__ uint2 gc_lds_volatile2(const uint2 *p)
 	asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(umma::smem_addr(p)) : "memory");
 	return v;
 }
-/* bounded spin (a protocol bug must not hang the device): ~2^28 polls of shared memory are seconds */
+/* bounded spin (a protocol bug must not hang the device): 2^28 polls of shared memory within one update are seconds */
 __device__ __forceinline__ void gc_spin(unsigned &n)
 {
 	if (++n > (1u << 28)) __trap();
@@ -154,6 +154,7 @@ template <int RW, int U, bool TOL> __global__ void __launch_bounds__(GC_THREADS,
 	for (int t = 0;; t++) {
 		const int cur = t & 1, nxt = cur ^ 1;
 		const bool last = (t == updates);
+		spins = 0; /* the bound is on the polls of ONE update, however long the solve */
 		const bool chk = TOL && !last && t == next_chk;
 		/* arrival flag of y_t in buffer cur: its k-th use (k = (t-1)/2) carries flag (k+1)&1 -- the first use 1, against the zeros the
 		 * buffer starts with; y_0 is there from the start */
