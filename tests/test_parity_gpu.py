@@ -586,6 +586,9 @@ def test_small_batches_run_one_cluster_per_problem(pqp, oracle32, oracle64, monk
             Yb, Ub, stb = s.solve(X[:B], iters=K, primal=True)
             assert s.last_kernel == "gemv_cluster_batch"
             assert np.array_equal(Yb, Y[:B]) and np.array_equal(Ub, U[:B]) and np.array_equal(stb["gap"], st["gap"][:B])
+        Ya, _, _ = s.solve(X[:7], iters=100)                          # warm start: the loop's only state is y
+        Yb, _, _ = s.solve(X[:7], iters=K - 100, Y0=Ya)
+        assert np.array_equal(Yb, Y[:7])
         Y1, U1, st1 = s.solve(X[3:4], iters=K, primal=True)
         assert s.last_kernel == "gemv_cluster" and np.array_equal(Y1[0], Y[3]) and np.array_equal(U1[0], U[3])
         assert st1["gap"][0] == st["gap"][3] and st1["Jd"][0] == st["Jd"][3] and st["iters"][3] == K
