@@ -147,9 +147,13 @@ template <int RW, int U, bool TOL> __global__ void __launch_bounds__(GC_THREADS,
 	int done = updates, converged = 0;
 	float s_min = 0.0f, s_gap = 0.0f, s_jd = 0.0f, s_kkt = 0.0f;
 	unsigned spins = 0;
-	float ym[RW]; /* the rows' own duals: this warp computed them, they need not come back through the exchange */
-#pragma unroll
-	for (int rw = 0; rw < RW; rw++) ym[rw] = rok[rw] ? __uint_as_float(sm.y[0][(int)rank * Rpad + rowl[rw]]) : 0.0f;
+	/* the row this LANE finishes (two rows per warp: lanes 16-31 the second) and its constants; its dual stays in a register: this warp
+	 * computed it, it need not come back through the exchange */
+	const int sel = (RW == 2 && lane >= 16) ? RW - 1 : 0;
+	const float th_l = th[sel], fdn_l = fdn[sel], fdp_l = fdp[sel], fd_l = fd[sel], tol_l = tolr[sel];
+	const bool rok_l = rok[sel];
+	const int rowl_l = rowl[sel];
+	float ym_l = rok_l ? __uint_as_float(sm.y[0][(int)rank * Rpad + rowl_l]) : 0.0f;
 
 	for (int t = 0;; t++) {
 		const int cur = t & 1, nxt = cur ^ 1;
@@ -235,34 +239,54 @@ template <int RW, int U, bool TOL> __global__ void __launch_bounds__(GC_THREADS,
 			num[rw] = n;
 			den[rw] = d;
 		}
+		/* row totals over the 32 lanes.  Two rows per warp: the first round also sorts them onto the two half-warps (lanes 0-15 end up
+		 * with row 0, lanes 16-31 with row 1), so the tree, the update and the division are issued once for both rows */
+		float n_t, d_t;
+		if (RW == 2) {
+			const bool hi = lane >= 16;
+			n_t = (hi ? num[RW - 1] : num[0]) + __shfl_xor_sync(0xffffffffu, hi ? num[0] : num[RW - 1], 16);
+			d_t = (hi ? den[RW - 1] : den[0]) + __shfl_xor_sync(0xffffffffu, hi ? den[0] : den[RW - 1], 16);
 #pragma unroll
-		for (int o = 16; o; o >>= 1)
-#pragma unroll
-			for (int rw = 0; rw < RW; rw++) {
-				num[rw] += __shfl_xor_sync(0xffffffffu, num[rw], o);
-				den[rw] += __shfl_xor_sync(0xffffffffu, den[rw], o);
+			for (int o = 8; o; o >>= 1) {
+				n_t += __shfl_xor_sync(0xffffffffu, n_t, o);
+				d_t += __shfl_xor_sync(0xffffffffu, d_t, o);
 			}
+		} else {
+			n_t = num[0];
+			d_t = den[0];
+#pragma unroll
+			for (int o = 16; o; o >>= 1) {
+				n_t += __shfl_xor_sync(0xffffffffu, n_t, o);
+				d_t += __shfl_xor_sync(0xffffffffu, d_t, o);
+			}
+		}
 		float e_min = INFINITY, e_gap = 0.0f, e_jd = 0.0f, e_kkt = 0.0f, e_viol = -INFINITY;
-#pragma unroll
-		for (int rw = 0; rw < RW; rw++) {
-			const float y_mine = ym[rw];
-			const float nn = fmaf(th[rw], y_mine, num[rw]) + fdn[rw];
-			const float dd = fmaf(th[rw], y_mine, den[rw]) + fdp[rw];
-			if ((last || chk) && rok[rw]) {
+		{
+			const float y_mine = ym_l;
+			const float nn = fmaf(th_l, y_mine, n_t) + fdn_l;
+			const float dd = fmaf(th_l, y_mine, d_t) + fdp_l;
+			if ((last || chk) && rok_l) {
 				const float gq = dd - nn;
-				e_min = fminf(e_min, gq);
-				e_gap += y_mine * gq;
-				e_jd += y_mine * (0.5f * (gq + fd[rw]));
-				e_kkt = fmaxf(e_kkt, fabsf(fminf(y_mine, gq)));
-				e_viol = fmaxf(e_viol, -gq - tolr[rw]);
+				e_min = gq;
+				e_gap = y_mine * gq;
+				e_jd = y_mine * (0.5f * (gq + fd_l));
+				e_kkt = fabsf(fminf(y_mine, gq));
+				e_viol = -gq - tol_l;
 			}
+			if (RW == 2 && (last || chk)) {
+				/* lane 0 folds its row, then the row of lane 16 */
+				const float m2 = __shfl_sync(0xffffffffu, e_min, 16), g2 = __shfl_sync(0xffffffffu, e_gap, 16), j2 = __shfl_sync(0xffffffffu, e_jd, 16),
+					    k2 = __shfl_sync(0xffffffffu, e_kkt, 16), v2 = __shfl_sync(0xffffffffu, e_viol, 16);
+				e_min = fminf(e_min, m2); e_gap += g2; e_jd += j2; e_kkt = fmaxf(e_kkt, k2); e_viol = fmaxf(e_viol, v2);
+			}
+			const bool writer = RW == 2 ? (lane & 15) == 0 : lane == 0;
 			if (last) {
-				if (lane == 0 && rok[rw]) a.ybuf1[(int)rank * R + rowl[rw]] = y_mine; /* the answer, as a plain vector */
+				if (writer && rok_l) a.ybuf1[(int)rank * R + rowl_l] = y_mine; /* the answer, as a plain vector */
 			} else {
 				/* (a NaN dual keeps its payload but not its sign: the bit carries the arrival flag) */
-				const float yn = rok[rw] ? __fdiv_rn(nn, dd) * y_mine : 0.0f;
-				ym[rw] = __uint_as_float(__float_as_uint(yn) & 0x7fffffffu);
-				if (lane == 0 && rowl[rw] < Rpad) sm.stage[nxt][rowl[rw]] = (__float_as_uint(yn) & 0x7fffffffu) | want_nxt; /* padding rows: zeros, flagged */
+				const float yn = rok_l ? __fdiv_rn(nn, dd) * y_mine : 0.0f;
+				ym_l = __uint_as_float(__float_as_uint(yn) & 0x7fffffffu);
+				if (writer && rowl_l < Rpad) sm.stage[nxt][rowl_l] = (__float_as_uint(yn) & 0x7fffffffu) | want_nxt; /* padding rows: zeros, flagged */
 			}
 		}
 		if (last || chk) {
@@ -417,7 +441,7 @@ int gc_size_for(int N)
 /* 64 < N: up to there one thread block does it without any exchange in 0.18-0.30 us per update (pqp_gemv_cta.cu; measured 0.97 at
  * N = 96 and 1.25 at N = 128, against 0.52 here).  Up to 32 rows per CTA (two per warp) and 512
  * padded columns, i.e. N <= 512 on a cluster of 16: beyond that the 16 SMs' arithmetic costs more than the exchange saves (measured:
- * N = 144..256 0.60 us per update against 0.95-1.00 for the multi-CTA kernel, N = 480 0.94 against 1.05, N = 640 slower). */
+ * N = 144..256 0.55-0.58 us per update against 0.95-1.00 for the multi-CTA kernel, N = 480 0.83 against 1.05, N = 640 slower). */
 int pqp_gemv_cluster_supported(int N)
 {
 	const char *e = pqp_env("PQP_GEMV_CLUSTER");
