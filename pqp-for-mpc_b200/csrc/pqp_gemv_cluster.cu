@@ -35,7 +35,7 @@
 #define GC_WARPS 16
 #define GC_MAXCS 16
 #ifndef GC_SMALL_N
-#define GC_SMALL_N 0 /* problems up to this size take a cluster of 8 (0: always the largest cluster) */
+#define GC_SMALL_N 128 /* problems up to this size take a cluster of 8: measured, one problem runs as fast (N = 96: 0.50 against 0.52 us per update) and twice as many clusters run at a time (16 problems: 0.98 against 1.5-1.6 ms per 1000 updates); at N = 144-256 a single problem is 10 % slower on 8 */
 #endif
 #define GC_MAXNP 512 /* padded length of y: 4 column groups of 128 */
 
